@@ -1,0 +1,254 @@
+// Class-aware greedy NMS for sm_100a, bit-exact with the CPU kernel the oracle runs.
+//
+// Replaces torchvision.ops.boxes.batched_nms / torchvision::nms as called from
+// detectron2/layers/nms.py:19-39 (call sites proposal_utils.py:116, fast_rcnn.py:184).
+//
+// Pipeline, all on the caller's stream, no host synchronisation:
+//   1. (coordinate-trick mode only) max over all coordinates               -> nms_max_kernel
+//   2. stable descending radix sort of (score, index)                      -> cub::DeviceRadixSort
+//   3. gather boxes (+ class offset) / class ids into sorted order          -> nms_gather_kernel
+//   4. 64x64-tile IoU bitmask, upper triangle only, warp-ballot rows        -> nms_mask_kernel
+//   5. greedy scan on the device: per 64-box block resolve the diagonal tile serially in registers,
+//      then OR the kept rows into the removed-bitmap in parallel; kept indices are emitted in order
+//                                                                          -> nms_scan_kernel
+// IoU arithmetic is fp32 without FMA contraction ((area_i + area_j) - inter, IEEE division) and the
+// threshold test promotes the fp32 IoU to double, exactly like the CPU kernel (oracle/c/nms_ref.c).
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace cddmsl {
+
+constexpr int kTile = 64;
+
+__global__ void nms_max_kernel(const float* __restrict__ boxes, int64_t n4, float* __restrict__ out_max) {
+  // single block; M*4 values.  -inf start; result is the exact max (order-independent).
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) m = fmaxf(m, boxes[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    m = warp_max(m);
+    if (threadIdx.x == 0) *out_max = m;
+  }
+}
+
+__global__ void nms_iota_kernel(const float* __restrict__ scores, float* __restrict__ keys, int* __restrict__ vals,
+                                int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) {
+    float s = scores[i];
+    keys[i] = (s == 0.f) ? 0.f : s;  // -0.0 and +0.0 compare equal in the reference's sort
+    vals[i] = i;
+  }
+}
+
+__global__ void nms_gather_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ idxs,
+                                  const int* __restrict__ order, const float* __restrict__ max_coord,
+                                  int coord_trick, float4* __restrict__ sboxes, int* __restrict__ scls, int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int o = order[i];
+  float4 b = boxes[o];
+  int cls = 0;
+  if (idxs) {
+    const int64_t id = idxs[o];
+    if (coord_trick) {
+      // offsets = idxs.to(boxes) * (max_coordinate + 1);  boxes + offsets[:, None]   (fp32, rn)
+      const float off = __fmul_rn((float)id, __fadd_rn(*max_coord, 1.0f));
+      b.x = __fadd_rn(b.x, off);
+      b.y = __fadd_rn(b.y, off);
+      b.z = __fadd_rn(b.z, off);
+      b.w = __fadd_rn(b.w, off);
+    } else {
+      cls = (int)id;
+    }
+  }
+  sboxes[i] = b;
+  scls[i] = cls;
+}
+
+__device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float area_a, float area_b, double thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return (double)ovr > thr;  // NaN (0/0) compares false: never suppresses
+}
+
+// grid (col_blocks, row_blocks), 64 threads; only tiles with col_block >= row_block are computed.
+__global__ void __launch_bounds__(kTile)
+nms_mask_kernel(const float4* __restrict__ sboxes, const int* __restrict__ scls, int M, double thr, int col_blocks,
+                unsigned long long* __restrict__ mask) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  __shared__ float4 cbox[kTile];
+  __shared__ float carea[kTile];
+  __shared__ int ccls[kTile];
+  const int ncol = min(M - cb * kTile, kTile);
+  if (threadIdx.x < ncol) {
+    const float4 b = sboxes[cb * kTile + threadIdx.x];
+    cbox[threadIdx.x] = b;
+    carea[threadIdx.x] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    ccls[threadIdx.x] = scls[cb * kTile + threadIdx.x];
+  }
+  __syncthreads();
+  const int i = rb * kTile + threadIdx.x;
+  if (i >= M) return;
+  const float4 a = sboxes[i];
+  const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const int cls_a = scls[i];
+  unsigned long long bits = 0ull;
+  const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+  for (int j = start; j < ncol; ++j) {
+    if (ccls[j] == cls_a && iou_over(a, cbox[j], area_a, carea[j], thr)) bits |= 1ull << j;
+  }
+  mask[(size_t)i * col_blocks + cb] = bits;
+}
+
+// One CTA.  remv[] (shared) = bitmap of suppressed boxes.  For block b: thread 0..63 fetch the diagonal
+// words, lane 0 of warp 0 resolves the block serially (64 dependent bit-ops), then every thread ORs the
+// rows of the kept boxes into its own column words.
+__global__ void __launch_bounds__(1024)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int M, int col_blocks,
+                int64_t* __restrict__ keep, int32_t* __restrict__ num_keep) {
+  extern __shared__ unsigned long long remv[];  // [col_blocks]
+  __shared__ unsigned long long diag[kTile];
+  __shared__ unsigned long long kept_s;
+  __shared__ int count_s;
+  for (int w = threadIdx.x; w < col_blocks; w += blockDim.x) remv[w] = 0ull;
+  if (threadIdx.x == 0) count_s = 0;
+  __syncthreads();
+  for (int b = 0; b < col_blocks; ++b) {
+    const int nb = min(M - b * kTile, kTile);
+    if (threadIdx.x < kTile)
+      diag[threadIdx.x] = threadIdx.x < nb ? mask[(size_t)(b * kTile + threadIdx.x) * col_blocks + b] : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long alive = ~remv[b];
+      if (nb < kTile) alive &= (1ull << nb) - 1ull;
+      unsigned long long kept = 0ull;
+      while (alive) {
+        const int t = __ffsll((long long)alive) - 1;
+        kept |= 1ull << t;
+        alive &= ~(diag[t] | (1ull << t));
+      }
+      kept_s = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = kept_s;
+    const int base = count_s;
+    if (threadIdx.x < kTile && ((kept >> threadIdx.x) & 1ull)) {
+      const int pos = base + __popcll(kept & ((1ull << threadIdx.x) - 1ull));
+      keep[pos] = (int64_t)order[b * kTile + threadIdx.x];
+    }
+    for (int w = b + 1 + threadIdx.x; w < col_blocks; w += blockDim.x) {
+      unsigned long long acc = 0ull, k = kept;
+      while (k) {
+        const int t = __ffsll((long long)k) - 1;
+        k &= k - 1ull;
+        acc |= mask[(size_t)(b * kTile + t) * col_blocks + w];
+      }
+      remv[w] |= acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count_s = base + __popcll(kept);
+    // (count_s is re-read after the next iteration's barriers)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *num_keep = count_s;
+}
+
+struct NmsWs {
+  float* keys_in;
+  float* keys_out;
+  int* vals_in;
+  int* order;
+  float4* sboxes;
+  int* scls;
+  float* max_coord;
+  unsigned long long* mask;
+  void* cub_temp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+static NmsWs carve(void* base, int64_t M) {
+  NmsWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t m = (size_t)(M > 0 ? M : 1);
+  const size_t cb = (m + kTile - 1) / kTile;
+  w.keys_in = (float*)take(m * 4);
+  w.keys_out = (float*)take(m * 4);
+  w.vals_in = (int*)take(m * 4);
+  w.order = (int*)take(m * 4);
+  w.sboxes = (float4*)take(m * 16);
+  w.scls = (int*)take(m * 4);
+  w.max_coord = (float*)take(4);
+  w.mask = (unsigned long long*)take(m * cb * 8);
+  w.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float*)nullptr, (float*)nullptr,
+                                            (const int*)nullptr, (int*)nullptr, (int)m, 0, 32, (cudaStream_t)0);
+  w.cub_temp = take(w.cub_bytes);
+  w.total = off;
+  return w;
+}
+
+}  // namespace cddmsl
+
+using namespace cddmsl;
+
+extern "C" size_t cddmsl_nms_workspace_bytes(int64_t M) { return carve(nullptr, M).total; }
+
+extern "C" int cddmsl_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
+                          double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep, void* workspace,
+                          size_t workspace_bytes, cddmsl_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (M < 0 || !num_keep) return CDDMSL_EINVAL;
+  if (M == 0) {
+    CDDMSL_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
+    return CDDMSL_OK;
+  }
+  if (M > (1 << 24)) return CDDMSL_EINVAL;
+  if (!boxes || !scores || !keep || !workspace) return CDDMSL_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(boxes) & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return CDDMSL_EALIGN;
+  NmsWs w = carve(workspace, M);
+  if (w.total > workspace_bytes) return CDDMSL_EWORKSPACE;
+  const int m = (int)M;
+  const int col_blocks = ceil_div(m, kTile);
+  if ((size_t)col_blocks * 8 > 200 * 1024) return CDDMSL_EINVAL;  // removed-bitmap must fit shared memory
+
+  if (idxs && coord_trick) {
+    nms_max_kernel<<<1, 1024, 0, stream>>>(boxes, (int64_t)m * 4, w.max_coord);
+    count_launch();
+  }
+  nms_iota_kernel<<<ceil_div(m, 256), 256, 0, stream>>>(scores, w.keys_in, w.vals_in, m);
+  count_launch();
+  CDDMSL_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, w.cub_bytes, w.keys_in, w.keys_out, w.vals_in,
+                                                        w.order, m, 0, 32, stream));
+  count_launch(3);  // histogram + onesweep passes (CUB internal; counted as one logical sort)
+  nms_gather_kernel<<<ceil_div(m, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(boxes), idxs, w.order,
+                                                           w.max_coord, coord_trick, w.sboxes, w.scls, m);
+  count_launch();
+  nms_mask_kernel<<<dim3(col_blocks, col_blocks), kTile, 0, stream>>>(w.sboxes, w.scls, m, iou_threshold,
+                                                                      col_blocks, w.mask);
+  count_launch();
+  const int smem = col_blocks * 8;
+  if (smem > 48 * 1024)
+    CDDMSL_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  nms_scan_kernel<<<1, 1024, smem, stream>>>(w.mask, w.order, m, col_blocks, keep, num_keep);
+  count_launch();
+  CDDMSL_CHECK_LAUNCH();
+  return CDDMSL_OK;
+}

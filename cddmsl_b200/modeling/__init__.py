@@ -1,0 +1,11 @@
+"""Host-side mirror of the reference modules that call the hot path."""
+from .box_regression import Box2BoxTransform
+from .caption_consistency import caption_consistency_loss, image_caption_consistency_loss
+from .fast_rcnn import FastRCNNOutputLayers, fast_rcnn_inference, fast_rcnn_inference_single_image
+from .gather import GatherLayer
+from .poolers import ROIPooler, convert_boxes_to_pooler_format
+from .proposal_utils import find_top_rpn_proposals
+
+__all__ = ["Box2BoxTransform", "caption_consistency_loss", "image_caption_consistency_loss",
+           "FastRCNNOutputLayers", "fast_rcnn_inference", "fast_rcnn_inference_single_image", "GatherLayer",
+           "ROIPooler", "convert_boxes_to_pooler_format", "find_top_rpn_proposals"]

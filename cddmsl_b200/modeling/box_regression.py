@@ -1,0 +1,48 @@
+"""Box2BoxTransform (detectron2/modeling/box_regression.py:18-117): the R-CNN box parameterisation.
+Plain tensor arithmetic, not on the hot path; here so that the box predictor mirror is self-contained."""
+import math
+from typing import Tuple
+
+import torch
+
+_DEFAULT_SCALE_CLAMP = math.log(1000.0 / 16)
+
+
+class Box2BoxTransform:
+    def __init__(self, weights: Tuple[float, float, float, float], scale_clamp: float = _DEFAULT_SCALE_CLAMP):
+        self.weights = weights
+        self.scale_clamp = scale_clamp
+
+    def get_deltas(self, src_boxes: torch.Tensor, target_boxes: torch.Tensor) -> torch.Tensor:
+        sw = src_boxes[:, 2] - src_boxes[:, 0]
+        sh = src_boxes[:, 3] - src_boxes[:, 1]
+        sx = src_boxes[:, 0] + 0.5 * sw
+        sy = src_boxes[:, 1] + 0.5 * sh
+        tw = target_boxes[:, 2] - target_boxes[:, 0]
+        th = target_boxes[:, 3] - target_boxes[:, 1]
+        tx = target_boxes[:, 0] + 0.5 * tw
+        ty = target_boxes[:, 1] + 0.5 * th
+        wx, wy, ww, wh = self.weights
+        deltas = torch.stack((wx * (tx - sx) / sw, wy * (ty - sy) / sh, ww * torch.log(tw / sw),
+                              wh * torch.log(th / sh)), dim=1)
+        assert (sw > 0).all().item(), "Input boxes to Box2BoxTransform are not valid!"
+        return deltas
+
+    def apply_deltas(self, deltas: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+        deltas = deltas.float()
+        boxes = boxes.to(deltas.dtype)
+        widths = boxes[:, 2] - boxes[:, 0]
+        heights = boxes[:, 3] - boxes[:, 1]
+        ctr_x = boxes[:, 0] + 0.5 * widths
+        ctr_y = boxes[:, 1] + 0.5 * heights
+        wx, wy, ww, wh = self.weights
+        dx = deltas[:, 0::4] / wx
+        dy = deltas[:, 1::4] / wy
+        dw = torch.clamp(deltas[:, 2::4] / ww, max=self.scale_clamp)
+        dh = torch.clamp(deltas[:, 3::4] / wh, max=self.scale_clamp)
+        pcx = dx * widths[:, None] + ctr_x[:, None]
+        pcy = dy * heights[:, None] + ctr_y[:, None]
+        pw = torch.exp(dw) * widths[:, None]
+        ph = torch.exp(dh) * heights[:, None]
+        pred = torch.stack((pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph), dim=-1)
+        return pred.reshape(deltas.shape)

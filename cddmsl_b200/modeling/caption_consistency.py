@@ -1,0 +1,63 @@
+"""Caption-consistency alignment loss (detectron2/modeling/meta_arch/rcnn.py:305-317 image level,
+:455-468 region level; the reference has no function boundary for it — the code is inline in
+`GeneralizedRCNN`).  One call replaces: 2x GatherLayer, 2x row normalisation, the n x n matmul, two
+cross-entropies and their autograd graph.
+
+Data-parallel semantics: each rank owns `n_local` rows of src and tgt; rows are normalised
+and packed locally, ONE all-gather (NCCL over NVLink) exchanges them, every rank evaluates the full
+symmetric InfoNCE and back-propagates only into its own rows — exactly what GatherLayer.backward
+(gather.py:16-20) yields.  No collective runs in backward.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+
+
+def shard_bounds(n_total: int, world: int, rank: int):
+    """Images (and all their RoIs / embedding rows) are split contiguously and evenly over ranks."""
+    assert n_total % world == 0, "the reference's sampler gives every rank the same number of images"
+    per = n_total // world
+    return rank * per, (rank + 1) * per
+
+
+class _CaptionConsistency(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, group):
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        packed, norms = ops.align_pack(a, b)
+        if world > 1:
+            packed_all = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+            dist.all_gather_into_tensor(packed_all, packed, group=group)
+        else:
+            packed_all = packed.unsqueeze(0)
+        loss, _, _ = ops.align_loss(packed_all, norms, rank, None, False)
+        ctx.save_for_backward(packed_all, norms)
+        ctx.rank = rank
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        packed_all, norms = ctx.saved_tensors
+        _, da, db = ops.align_loss(packed_all, norms, ctx.rank, gloss.reshape(1), True)
+        return da, db, None
+
+
+def caption_consistency_loss(src: torch.Tensor, tgt: torch.Tensor,
+                             group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
+    """rcnn.py:455-468: `S = norm(gather(src)) @ norm(gather(tgt)).T`, `(CE(S, I) + CE(S.T, I)) / 2`.
+    src, tgt: this rank's [n_local, D] projector outputs."""
+    assert src.dim() == 2 and src.shape == tgt.shape
+    return _CaptionConsistency.apply(src, tgt, group)
+
+
+def image_caption_consistency_loss(trgt: torch.Tensor, src: torch.Tensor,
+                                   group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
+    """rcnn.py:305-317 (`v2l_contrastive` tail): same loss with the operands in the reference's order,
+    `joint = trgt @ src.T` (the loss is symmetric in the pair, gradients follow the operands)."""
+    return caption_consistency_loss(trgt, src, group)

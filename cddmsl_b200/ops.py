@@ -1,0 +1,287 @@
+"""PyTorch custom ops (`torch.ops.cddmsl_b200.*`) over the C ABI of include/cddmsl_b200.h.
+
+Each op is a thin shim: validate, allocate outputs/workspace with the caching allocator, hand raw device
+pointers + the current CUDA stream to the library.  Autograd is registered on the ops, so the reference's
+call sites (`detectron2.layers.ROIAlign`, the box predictor, the consistency loss) differentiate through
+them unchanged.  CUDA only — a CPU tensor raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+LOSS_FOCAL, LOSS_CE, LOSS_WEIGHTED_CE = 0, 1, 2
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------ ROIAlign
+@torch.library.custom_op("cddmsl_b200::roi_align", mutates_args=(), device_types="cuda")
+def roi_align(input: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int, pooled_width: int,
+              sampling_ratio: int, aligned: bool) -> Tensor:
+    _lib.require_cuda(input, "input")
+    _lib.require_cuda(rois, "rois")
+    x, r = _f32c(input), _f32c(rois)
+    n, c, h, w = x.shape
+    nr = r.shape[0]
+    out = torch.empty((nr, c, pooled_height, pooled_width), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().cddmsl_roi_align_fwd(_lib.ptr(x), _lib.ptr(r), _lib.ptr(out), n, c, h, w, nr,
+                                                   pooled_height, pooled_width, spatial_scale, sampling_ratio,
+                                                   int(aligned), _lib.stream_ptr(x.device)), "roi_align_fwd")
+    return out if input.dtype == torch.float32 else out.to(input.dtype)
+
+
+@roi_align.register_fake
+def _(input, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio, aligned):
+    return input.new_empty((rois.shape[0], input.shape[1], pooled_height, pooled_width))
+
+
+@torch.library.custom_op("cddmsl_b200::roi_align_backward", mutates_args=(), device_types="cuda")
+def roi_align_backward(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int, pooled_width: int,
+                       batch_size: int, channels: int, height: int, width: int, sampling_ratio: int,
+                       aligned: bool) -> Tensor:
+    _lib.require_cuda(grad, "grad")
+    g, r = _f32c(grad), _f32c(rois)
+    nr = r.shape[0]
+    gin = torch.empty((batch_size, channels, height, width), dtype=torch.float32, device=g.device)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_roi_align_bwd_workspace_bytes(batch_size, channels, height, width, nr), g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(L.cddmsl_roi_align_bwd(_lib.ptr(g), _lib.ptr(r), _lib.ptr(gin), batch_size, channels, height,
+                                          width, nr, pooled_height, pooled_width, spatial_scale, sampling_ratio,
+                                          int(aligned), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(g.device)),
+                   "roi_align_bwd")
+    return gin if grad.dtype == torch.float32 else gin.to(grad.dtype)
+
+
+@roi_align_backward.register_fake
+def _(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width,
+      sampling_ratio, aligned):
+    return grad.new_empty((batch_size, channels, height, width))
+
+
+def _roi_align_setup(ctx, inputs, output):
+    input, rois, scale, ph, pw, sr, aligned = inputs
+    ctx.save_for_backward(rois)
+    ctx.meta = (scale, ph, pw, tuple(input.shape), sr, aligned)
+
+
+def _roi_align_bwd(ctx, grad):
+    (rois,) = ctx.saved_tensors
+    scale, ph, pw, (n, c, h, w), sr, aligned = ctx.meta
+    gin = None
+    if ctx.needs_input_grad[0]:
+        gin = roi_align_backward(grad, rois, scale, ph, pw, n, c, h, w, sr, aligned)
+    return gin, None, None, None, None, None, None
+
+
+roi_align.register_autograd(_roi_align_bwd, setup_context=_roi_align_setup)
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+@torch.library.custom_op("cddmsl_b200::batched_nms", mutates_args=(), device_types="cuda")
+def batched_nms(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float,
+                coord_trick: bool) -> Tensor:
+    """Kept original indices, score-descending (ties: lower index first).  One device->host read of the
+    kept count sizes the result (the same sync PyTorch needs for any data-dependent shape)."""
+    _lib.require_cuda(boxes, "boxes")
+    b = _f32c(boxes)
+    s = _f32c(scores)
+    m = b.shape[0]
+    if m == 0:
+        return torch.empty((0,), dtype=torch.int64, device=b.device)
+    ids = None if idxs is None else idxs.to(torch.int64).contiguous()
+    L = _lib.lib()
+    keep = torch.empty((m,), dtype=torch.int64, device=b.device)
+    nk = torch.empty((1,), dtype=torch.int32, device=b.device)
+    ws = _ws(L.cddmsl_nms_workspace_bytes(m), b.device)
+    with torch.cuda.device(b.device):
+        _lib.check(L.cddmsl_nms(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), m, float(iou_threshold), int(coord_trick),
+                                _lib.ptr(keep), _lib.ptr(nk), _lib.ptr(ws), ws.numel(),
+                                _lib.stream_ptr(b.device)), "nms")
+    return keep[: int(nk.item())]
+
+
+@batched_nms.register_fake
+def _(boxes, scores, idxs, iou_threshold, coord_trick):
+    n = torch.library.get_ctx().new_dynamic_size()
+    return boxes.new_empty((n,), dtype=torch.int64)
+
+
+# ------------------------------------------------------------------------------------------ CLIP head
+def _head_ws(r, d, k, device):
+    return _ws(_lib.lib().cddmsl_clip_head_workspace_bytes(r, d, k), device)
+
+
+@torch.library.custom_op("cddmsl_b200::clip_head_scores", mutates_args=(), device_types="cuda")
+def clip_head_scores(x: Tensor, weight: Tensor, bg_weight: Tensor, temperature: float) -> Tensor:
+    _lib.require_cuda(x, "x")
+    xx, w, wb = _f32c(x), _f32c(weight), _f32c(bg_weight).reshape(-1)
+    r, d = xx.shape
+    k = w.shape[0]
+    scores = torch.empty((r, k + 1), dtype=torch.float32, device=xx.device)
+    ws = _head_ws(r, d, k, xx.device)
+    with torch.cuda.device(xx.device):
+        _lib.check(_lib.lib().cddmsl_clip_head_scores(_lib.ptr(xx), _lib.ptr(w), _lib.ptr(wb), r, d, k, temperature,
+                                                      _lib.ptr(scores), _lib.ptr(ws), ws.numel(),
+                                                      _lib.stream_ptr(xx.device)), "clip_head_scores")
+    return scores
+
+
+@clip_head_scores.register_fake
+def _(x, weight, bg_weight, temperature):
+    return x.new_empty((x.shape[0], weight.shape[0] + 1))
+
+
+@torch.library.custom_op("cddmsl_b200::clip_head_scores_backward", mutates_args=(), device_types="cuda")
+def clip_head_scores_backward(x: Tensor, weight: Tensor, bg_weight: Tensor, dscores: Tensor,
+                              temperature: float) -> Tensor:
+    xx, w, wb, ds = _f32c(x), _f32c(weight), _f32c(bg_weight).reshape(-1), _f32c(dscores)
+    r, d = xx.shape
+    k = w.shape[0]
+    dx = torch.empty_like(xx)
+    ws = _head_ws(r, d, k, xx.device)
+    with torch.cuda.device(xx.device):
+        _lib.check(_lib.lib().cddmsl_clip_head_scores_bwd(_lib.ptr(xx), _lib.ptr(w), _lib.ptr(wb), _lib.ptr(ds), r, d,
+                                                          k, temperature, _lib.ptr(dx), _lib.ptr(ws), ws.numel(),
+                                                          _lib.stream_ptr(xx.device)), "clip_head_scores_bwd")
+    return dx
+
+
+@clip_head_scores_backward.register_fake
+def _(x, weight, bg_weight, dscores, temperature):
+    return torch.empty_like(x)
+
+
+def _scores_setup(ctx, inputs, output):
+    x, weight, bg_weight, temperature = inputs
+    ctx.save_for_backward(x, weight, bg_weight)
+    ctx.temperature = temperature
+
+
+def _scores_bwd(ctx, ds):
+    x, weight, bg_weight = ctx.saved_tensors
+    dx = clip_head_scores_backward(x, weight, bg_weight, ds, ctx.temperature) if ctx.needs_input_grad[0] else None
+    # concept / background embeddings are frozen in the reference (fast_rcnn.py:453,461)
+    return dx, None, None, None
+
+
+clip_head_scores.register_autograd(_scores_bwd, setup_context=_scores_setup)
+
+
+@torch.library.custom_op("cddmsl_b200::clip_head_loss", mutates_args=(), device_types="cuda")
+def clip_head_loss(x: Tensor, weight: Tensor, bg_weight: Tensor, gt: Tensor, temperature: float, loss_mode: int,
+                   gamma: float, bg_cls_weight: float, grad_scale: Optional[Tensor], strict_nan: bool,
+                   want_scores: bool, want_dx: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Fused logits -> loss (-> dx).  Returns (loss[], scores[R,K+1] or empty, dx[R,D] or empty, stats int32[4])."""
+    _lib.require_cuda(x, "x")
+    xx, w, wb = _f32c(x), _f32c(weight), _f32c(bg_weight).reshape(-1)
+    g = gt.to(torch.int64).contiguous()
+    r, d = xx.shape
+    k = w.shape[0]
+    dev = xx.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    scores = torch.empty((r, k + 1) if want_scores else (0,), dtype=torch.float32, device=dev)
+    dx = torch.empty((r, d) if want_dx else (0,), dtype=torch.float32, device=dev)
+    stats = torch.empty((4,), dtype=torch.int32, device=dev)
+    gs = None if grad_scale is None else _f32c(grad_scale)
+    ws = _head_ws(r, d, k, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cddmsl_clip_head_loss(
+            _lib.ptr(xx), _lib.ptr(w), _lib.ptr(wb), _lib.ptr(g), r, d, k, temperature, loss_mode, gamma,
+            bg_cls_weight, _lib.ptr(gs), int(strict_nan), _lib.ptr(scores) if want_scores else None, _lib.ptr(loss),
+            _lib.ptr(dx) if want_dx else None, _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+            "clip_head_loss")
+    return loss, scores, dx, stats
+
+
+@clip_head_loss.register_fake
+def _(x, weight, bg_weight, gt, temperature, loss_mode, gamma, bg_cls_weight, grad_scale, strict_nan, want_scores,
+      want_dx):
+    r, d = x.shape
+    k = weight.shape[0]
+    return (x.new_empty(()), x.new_empty((r, k + 1) if want_scores else (0,)),
+            x.new_empty((r, d) if want_dx else (0,)), x.new_empty((4,), dtype=torch.int32))
+
+
+def _loss_setup(ctx, inputs, output):
+    x, weight, bg_weight, gt, temperature, loss_mode, gamma, bg_cls_weight, _gs, strict_nan, _ws_, _wd = inputs
+    ctx.save_for_backward(x, weight, bg_weight, gt)
+    ctx.meta = (temperature, loss_mode, gamma, bg_cls_weight, strict_nan)
+
+
+def _loss_bwd(ctx, gloss, gscores, gdx, gstats):
+    x, weight, bg_weight, gt = ctx.saved_tensors
+    t, mode, gamma, bgw, strict = ctx.meta
+    dx = None
+    if ctx.needs_input_grad[0]:
+        # recompute from x with the upstream scalar folded in: 1 read of x + 1 write of dx
+        _, _, dx, _ = clip_head_loss(x, weight, bg_weight, gt, t, mode, gamma, bgw, gloss.reshape(1), strict,
+                                     False, True)
+    return (dx,) + (None,) * 11
+
+
+clip_head_loss.register_autograd(_loss_bwd, setup_context=_loss_setup)
+
+
+# ------------------------------------------------------------------------------------ alignment loss
+@torch.library.custom_op("cddmsl_b200::align_pack", mutates_args=(), device_types="cuda")
+def align_pack(src: Tensor, tgt: Tensor) -> Tuple[Tensor, Tensor]:
+    _lib.require_cuda(src, "src")
+    a, b = _f32c(src), _f32c(tgt)
+    n, d = a.shape
+    packed = torch.empty((2, n, d), dtype=torch.float32, device=a.device)
+    norms = torch.empty((2, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().cddmsl_align_pack_normalized(_lib.ptr(a), _lib.ptr(b), n, d, _lib.ptr(packed),
+                                                           _lib.ptr(norms), _lib.stream_ptr(a.device)),
+                   "align_pack_normalized")
+    return packed, norms
+
+
+@align_pack.register_fake
+def _(src, tgt):
+    n, d = src.shape
+    return src.new_empty((2, n, d)), src.new_empty((2, n))
+
+
+@torch.library.custom_op("cddmsl_b200::align_loss", mutates_args=(), device_types="cuda")
+def align_loss(packed_all: Tensor, norms_local: Tensor, rank: int, grad_scale: Optional[Tensor],
+               want_grads: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """packed_all [world,2,n_local,D] (normalised rows).  Returns (loss[], da, db [n_local,D] or empty)."""
+    _lib.require_cuda(packed_all, "packed_all")
+    p = _f32c(packed_all)
+    world, two, n_local, d = p.shape
+    assert two == 2
+    dev = p.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    shape = (n_local, d) if want_grads else (0,)
+    da = torch.empty(shape, dtype=torch.float32, device=dev)
+    db = torch.empty(shape, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_align_loss_workspace_bytes(world, n_local, d), dev)
+    gs = None if grad_scale is None else _f32c(grad_scale)
+    with torch.cuda.device(dev):
+        _lib.check(L.cddmsl_align_loss(_lib.ptr(p), _lib.ptr(_f32c(norms_local)), world, n_local, d, rank,
+                                       _lib.ptr(gs), _lib.ptr(loss), _lib.ptr(da) if want_grads else None,
+                                       _lib.ptr(db) if want_grads else None, _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr(dev)), "align_loss")
+    return loss, da, db
+
+
+@align_loss.register_fake
+def _(packed_all, norms_local, rank, grad_scale, want_grads):
+    world, _, n_local, d = packed_all.shape
+    shape = (n_local, d) if want_grads else (0,)
+    return packed_all.new_empty(()), packed_all.new_empty(shape), packed_all.new_empty(shape)

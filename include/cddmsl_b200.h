@@ -1,0 +1,115 @@
+/*
+ * cddmsl_b200 — C ABI of the B200-native region-level vision-language hot path of CDDMSL.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry
+ * point enqueues work on the given CUDA stream and returns immediately (no hidden device synchronise);
+ * all buffers, including workspaces, are owned by the caller (PyTorch's caching allocator in practice) and
+ * outputs are fully overwritten.  All floating tensors are fp32, contiguous; indices are int64.
+ *
+ * Return value: 0 on success; otherwise a negative CDDMSL_E* shape/argument code or a positive
+ * cudaError_t.  `cddmsl_error_string()` renders either.  The Python host layer raises RuntimeError.
+ *
+ * Reference interfaces replaced (paths relative to the upstream checkout):
+ *   cddmsl_roi_align_fwd / _bwd   torchvision::roi_align / ::_roi_align_backward as called from
+ *                                 detectron2/layers/roi_align.py:49-65 (autograd backward of the same op)
+ *   cddmsl_nms                    torchvision.ops.boxes.batched_nms / torchvision::nms as called from
+ *                                 detectron2/layers/nms.py:19-39
+ *   cddmsl_clip_head_*            detectron2/modeling/roi_heads/fast_rcnn.py:543-565 (cosine logits),
+ *                                 :624-644 + layers/wrappers.py:26-33 (focal / weighted CE), :100-127 (stats)
+ *   cddmsl_align_loss_*           detectron2/modeling/meta_arch/rcnn.py:305-317, :455-468 (+ gather.py:5-20)
+ */
+#ifndef CDDMSL_B200_H_
+#define CDDMSL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cddmsl_stream_t; /* a cudaStream_t */
+
+enum {
+  CDDMSL_OK = 0,
+  CDDMSL_EINVAL = -1,     /* bad shape / null pointer / unsupported size */
+  CDDMSL_EWORKSPACE = -2, /* workspace too small */
+  CDDMSL_EALIGN = -3      /* pointer not aligned as required */
+};
+
+int cddmsl_abi_version(void);
+const char* cddmsl_error_string(int code);
+/* number of kernels this library has launched in this process (all entry points); bench.py's
+ * `gpu_launches` is the difference of two reads. */
+uint64_t cddmsl_launch_count(void);
+
+/* ---------------------------------------------------------------- piece 1: ROIAlign ------------- */
+/* in [N,C,H,W], rois [R,5] = (batch_idx, x0, y0, x1, y1) in image coordinates, out [R,C,PH,PW]. */
+int cddmsl_roi_align_fwd(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R,
+                         int PH, int PW, float spatial_scale, int sampling_ratio, int aligned,
+                         cddmsl_stream_t stream);
+
+/* gout [R,C,PH,PW] -> gin [N,C,H,W] (fully overwritten; zeroing happens inside). */
+size_t cddmsl_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R);
+int cddmsl_roi_align_bwd(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R,
+                         int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, void* workspace,
+                         size_t workspace_bytes, cddmsl_stream_t stream);
+
+/* ---------------------------------------------------------------- piece 2: NMS ------------------ */
+/* boxes [M,4] xyxy, scores [M], idxs [M] class/level ids or NULL.  keep [M] receives the kept ORIGINAL
+ * indices ordered by score descending (ties: lower index first); *num_keep (device int32) their count.
+ * iou_threshold is a double and the fp32 IoU is promoted before the strict `>` test, like the CPU kernel
+ * the oracle runs.  coord_trick != 0 reproduces torchvision's `_batched_nms_coordinate_trick`
+ * (boxes + idx * (max_coord + 1) in fp32), 0 the per-class loop (`_batched_nms_vanilla`, nms.py:32-39). */
+size_t cddmsl_nms_workspace_bytes(int64_t M);
+int cddmsl_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M, double iou_threshold,
+               int coord_trick, int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+               cddmsl_stream_t stream);
+
+/* ---------------------------------------------------------------- piece 3: CLIP box predictor --- */
+/* loss modes */
+enum { CDDMSL_LOSS_FOCAL = 0, CDDMSL_LOSS_CE = 1, CDDMSL_LOSS_WEIGHTED_CE = 2 };
+
+/* scores[R,K+1] = [ x^ . w^_k | x^ . w_bg ] / T   (x^ = x / max(|x|, 1e-12), w^ likewise).
+ * w [K,D] raw concept embeddings, w_bg [D] raw background embedding. */
+size_t cddmsl_clip_head_workspace_bytes(int R, int D, int K);
+int cddmsl_clip_head_scores(const float* x, const float* w, const float* w_bg, int R, int D, int K,
+                            float temperature, float* scores, void* workspace, size_t workspace_bytes,
+                            cddmsl_stream_t stream);
+/* dscores [R,K+1] -> dx [R,D] through the cosine logits. */
+int cddmsl_clip_head_scores_bwd(const float* x, const float* w, const float* w_bg, const float* dscores, int R,
+                                int D, int K, float temperature, float* dx, void* workspace,
+                                size_t workspace_bytes, cddmsl_stream_t stream);
+/* Fused logits -> softmax -> (focal | CE | weighted CE) loss -> gradient.
+ *   gt [R] int64 in [0,K] (K = background);  gamma: focal exponent (mode FOCAL);  bg_weight: weight of
+ *   class K (< 0: no class weighting);  grad_scale: device pointer to the upstream dL/dloss (NULL = 1).
+ *   scores (nullable) [R,K+1];  loss: device float;  dx (nullable) [R,D];  stats (nullable) device
+ *   int32[4] = {num_accurate, num_fg, fg_num_accurate, num_false_negative} (fast_rcnn.py:100-127).
+ *   strict_nan != 0 reproduces autograd's NaN gradient for rows whose softmax saturates to p_t == 1
+ *   under the focal loss; 0 emits the analytic limit (0). */
+int cddmsl_clip_head_loss(const float* x, const float* w, const float* w_bg, const int64_t* gt, int R, int D,
+                          int K, float temperature, int loss_mode, float gamma, float bg_weight,
+                          const float* grad_scale, int strict_nan, float* scores, float* loss, float* dx,
+                          int32_t* stats, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+
+/* ---------------------------------------------------------------- piece 4: alignment loss ------- */
+/* Row-normalise src|tgt [n_local,D] each (x / |x|, no eps — rcnn.py:308-309, :458-459) and pack them as
+ * packed[2][n_local][D] for ONE all-gather per branch (the reference issues two, rcnn.py:455-456;
+ * normalisation is row-local so it commutes with the gather).  norms[2][n_local] keeps |row| for the
+ * backward. */
+int cddmsl_align_pack_normalized(const float* src, const float* tgt, int n_local, int D, float* packed,
+                                 float* norms, cddmsl_stream_t stream);
+/* packed_all [world][2][n_local][D]: what all_gather makes of every rank's `packed` (world = 1: the local
+ * buffer itself).  loss = (CE(S, I) + CE(S^T, I)) / 2 with S = A^ B^T over all n = world*n_local rows, no
+ * temperature.  Gradients w.r.t. the UN-normalised local rows (rank*n_local ...) only — GatherLayer.backward
+ * keeps the local slice, gather.py:16-20 — into da, db [n_local,D] (both nullable).  grad_scale: device
+ * pointer to the upstream dL/dloss (NULL = 1). */
+size_t cddmsl_align_loss_workspace_bytes(int world, int n_local, int D);
+int cddmsl_align_loss(const float* packed_all, const float* norms_local, int world, int n_local, int D, int rank,
+                      const float* grad_scale, float* loss, float* da, float* db, void* workspace,
+                      size_t workspace_bytes, cddmsl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDDMSL_B200_H_ */

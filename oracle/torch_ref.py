@@ -1,0 +1,194 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product package `cddmsl_b200`.
+
+CPU restatement (`MODEL.DEVICE=cpu` semantics) of the reference's region-level hot path, written the
+way the reference calls it: torchvision CPU C++ ops + ATen CPU ops, fp32, indices int64.  Every function
+cites the reference lines it follows (paths relative to the upstream checkout).
+
+Why a restatement and not an import: the `detectron2` package of the reference cannot be imported
+(fvcore / yacs / iopath … absent, `*.cpp` sources git-ignored) and `/root/reference`
+does not exist on the GPU box.  The leaf files that *can* be loaded by path (`layers/roi_align.py`,
+`layers/wrappers.py`, `backbone/clipcap/gather.py`) were used in the build container to generate the
+fixtures under `tests/golden/` (see `tests/golden/make_golden.py`), which pin this file.
+
+Pinning status:
+  * ROIAlign  — pinned by the reference's golden vectors (tests/layers/test_roi_align.py:14-47,111-128)
+                and by reference-wrapper outputs on seeded inputs (tests/golden/roi_align_*.npz).
+  * NMS       — the reference holds no golden indices (tests/layers/test_nms.py:16-29 is a
+                self-consistency test); pinned by outputs of the installed torchvision CPU op, which is
+                the reference's arithmetic (tests/golden/nms_*.npz).
+  * CLIP head, focal loss, alignment loss, GatherLayer — **parity unpinned by the reference**: it has no
+    test for them.  They are pinned only to this restatement of the cited lines (and the
+    GatherLayer file loaded verbatim when the fixtures were generated).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs may
+import this module.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------- piece 1
+def roi_align(input: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale: float,
+              sampling_ratio: int, aligned: bool = True) -> torch.Tensor:
+    """detectron2/layers/roi_align.py:49-65 — assert [R,5], cast rois to the input dtype, call
+    torchvision's op (autograd -> `_roi_align_backward`)."""
+    from torchvision.ops import roi_align as tv_roi_align
+
+    assert rois.dim() == 2 and rois.size(1) == 5
+    return tv_roi_align(input, rois.to(dtype=input.dtype), output_size, spatial_scale, sampling_ratio,
+                        aligned)
+
+
+def convert_boxes_to_pooler_format(box_lists: Sequence[torch.Tensor]) -> torch.Tensor:
+    """detectron2/modeling/poolers.py:61-95 — per image prepend the batch index column, concatenate."""
+    out = []
+    for i, b in enumerate(box_lists):
+        out.append(torch.cat((torch.full_like(b[:, :1], i), b), dim=1))
+    return out[0] if len(out) == 1 else torch.cat(out, dim=0)
+
+
+def roi_pooler(x: torch.Tensor, box_lists: Sequence[torch.Tensor], output_size=(14, 14),
+               scale: float = 1.0 / 16, sampling_ratio: int = 0) -> torch.Tensor:
+    """detectron2/modeling/poolers.py:190-229 single-level path with POOLER_TYPE "ROIAlignV2"
+    (aligned=True, poolers.py:154-160; defaults config/defaults.py:423-426)."""
+    if len(box_lists) == 0:
+        return torch.zeros((0, x.shape[1]) + tuple(output_size), dtype=x.dtype)
+    return roi_align(x, convert_boxes_to_pooler_format(box_lists), output_size, scale, sampling_ratio, True)
+
+
+# --------------------------------------------------------------------------------------- piece 2
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float):
+    """detectron2/layers/nms.py:19-39."""
+    from torchvision.ops import boxes as box_ops
+    from torchvision.ops import nms
+
+    assert boxes.shape[-1] == 4
+    if len(boxes) < 40000:
+        return box_ops.batched_nms(boxes.float(), scores, idxs, iou_threshold)
+    result_mask = scores.new_zeros(scores.size(), dtype=torch.bool)
+    for cid in torch.unique(idxs).cpu().tolist():
+        mask = (idxs == cid).nonzero().view(-1)
+        keep = nms(boxes[mask], scores[mask], iou_threshold)
+        result_mask[mask[keep]] = True
+    keep = result_mask.nonzero().view(-1)
+    return keep[scores[keep].argsort(descending=True)]
+
+
+def find_top_rpn_proposals_single_image(boxes: torch.Tensor, scores: torch.Tensor, image_size: Tuple[int, int],
+                                        nms_thresh: float, post_nms_topk: int, min_box_size: float = 0.0,
+                                        training: bool = True):
+    """detectron2/modeling/proposal_generator/proposal_utils.py:95-130 for one image, one level
+    (`lvl == 0` for C4): finite check, clip, nonempty filter, batched_nms, post-NMS top-k."""
+    lvl = torch.zeros(len(boxes), dtype=torch.int64)
+    valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores)
+    if not valid.all():
+        if training:
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+        boxes, scores, lvl = boxes[valid], scores[valid], lvl[valid]
+    h, w = image_size
+    boxes = boxes.clone()
+    boxes[:, 0].clamp_(min=0, max=w)  # structures/boxes.py:192-206
+    boxes[:, 1].clamp_(min=0, max=h)
+    boxes[:, 2].clamp_(min=0, max=w)
+    boxes[:, 3].clamp_(min=0, max=h)
+    keep = ((boxes[:, 2] - boxes[:, 0]) > min_box_size) & ((boxes[:, 3] - boxes[:, 1]) > min_box_size)
+    if keep.sum().item() != len(boxes):
+        boxes, scores, lvl = boxes[keep], scores[keep], lvl[keep]
+    keep = batched_nms(boxes, scores, lvl, nms_thresh)[:post_nms_topk]
+    return boxes[keep], scores[keep]
+
+
+# --------------------------------------------------------------------------------------- piece 3
+def clip_head_scores(x: torch.Tensor, cls_weight: torch.Tensor, bg_weight: torch.Tensor,
+                     temperature: float) -> torch.Tensor:
+    """detectron2/modeling/roi_heads/fast_rcnn.py:543-565 (use_clip_cls_emb branch, use_bias False):
+    normalised x against normalised concept embeddings, background logit from the *un-normalised*
+    bg embedding (an nn.Linear, :560), concatenate, divide by the temperature."""
+    if x.dim() > 2:
+        x = torch.flatten(x, start_dim=1)
+    nx = F.normalize(x, p=2.0, dim=1)
+    cls = nx @ F.normalize(cls_weight, p=2.0, dim=1).t()
+    bg = F.linear(nx, bg_weight)
+    return torch.cat((cls, bg), dim=1) / temperature
+
+
+def focal_loss(scores: torch.Tensor, targets: torch.Tensor, num_classes: int, gamma: float = 0.5,
+               bg_weight: Optional[float] = None) -> torch.Tensor:
+    """fast_rcnn.py:624-644 — CE * (1 - p_t)^gamma, per-sample bg weight, plain mean over R.
+    Empty input: the reference raises AttributeError (`input.sum()` on the builtin, :626-627); the
+    documented drop-in behaviour is the gradient-connected zero of wrappers.py:31-32."""
+    if targets.numel() == 0:
+        return scores.sum() * 0.0
+    ce = F.cross_entropy(scores, targets, reduction="none")
+    p = F.softmax(scores, dim=-1)
+    p_t = p[torch.arange(p.size(0)), targets]
+    loss = ce * ((1 - p_t) ** gamma)
+    if bg_weight is not None:
+        w = torch.ones(loss.size(0))
+        w[targets == num_classes] = bg_weight
+        loss = loss * w
+    return loss.mean()
+
+
+def cls_loss(scores, targets, num_classes, focal_gamma: Optional[float], bg_weight: Optional[float]):
+    """fast_rcnn.py:608-615 — focal branch when FOCAL_SCALED_LOSS is set, else (weighted) CE through
+    layers/wrappers.py:26-33."""
+    if focal_gamma is not None:
+        return focal_loss(scores, targets, num_classes, focal_gamma, bg_weight)
+    if targets.numel() == 0:
+        return scores.sum() * 0.0
+    if bg_weight is None:
+        return F.cross_entropy(scores, targets, reduction="mean")
+    w = torch.ones(num_classes + 1)
+    w[-1] = bg_weight
+    return F.cross_entropy(scores, targets, reduction="mean", weight=w)
+
+
+def classification_stats(scores: torch.Tensor, gt: torch.Tensor) -> Tuple[int, int, int, int]:
+    """fast_rcnn.py:100-127 — (num_accurate, num_fg, fg_num_accurate, num_false_negative)."""
+    pred = scores.argmax(dim=1)
+    bg = scores.shape[1] - 1
+    fg = (gt >= 0) & (gt < bg)
+    return (int((pred == gt).sum()), int(fg.sum()), int((pred[fg] == gt[fg]).sum()),
+            int((pred[fg] == bg).sum()))
+
+
+# --------------------------------------------------------------------------------------- piece 4
+def caption_consistency_loss(a_all: torch.Tensor, b_all: torch.Tensor) -> torch.Tensor:
+    """detectron2/modeling/meta_arch/rcnn.py:458-468 (region level; :308-317 is the image-level twin
+    with the operands named trgt/src): rows divided by their norm (no eps), S = A @ B^T, symmetric
+    cross-entropy against the diagonal, no temperature."""
+    a = a_all / a_all.norm(dim=1, keepdim=True)
+    b = b_all / b_all.norm(dim=1, keepdim=True)
+    s = a @ b.t()
+    gt = torch.arange(len(s), dtype=torch.long)
+    return (F.cross_entropy(s, gt) + F.cross_entropy(s.t(), gt)) / 2
+
+
+def caption_consistency_world(a_locals: List[torch.Tensor], b_locals: List[torch.Tensor]):
+    """Single-process emulation of W ranks running rcnn.py:455-468 with
+    detectron2/modeling/backbone/clipcap/gather.py:5-20: every rank gathers all slices, computes the
+    full loss, and its backward keeps only the gradient of its *own* slice (no reduction).
+    Returns (loss, [grad_a_rank], [grad_b_rank])."""
+    world = len(a_locals)
+    ga, gb, loss_val = [], [], None
+    for rank in range(world):
+        a_parts = [t.detach().clone() for t in a_locals]
+        b_parts = [t.detach().clone() for t in b_locals]
+        a_parts[rank].requires_grad_(True)
+        b_parts[rank].requires_grad_(True)
+        loss = caption_consistency_loss(torch.cat(a_parts, 0), torch.cat(b_parts, 0))
+        loss.backward()
+        ga.append(a_parts[rank].grad)
+        gb.append(b_parts[rank].grad)
+        loss_val = loss.detach()
+    return loss_val, ga, gb
+
+
+def kd_l1_loss(teacher: torch.Tensor, student: torch.Tensor) -> torch.Tensor:
+    """rcnn.py:265-272 — L1Loss(teacher.detach(), student) (mean reduction)."""
+    return F.l1_loss(teacher.detach(), student)

@@ -1,0 +1,200 @@
+"""Generates the fixtures in this directory.  Run ONLY in the build container, where the upstream
+checkout is mounted at /root/reference:
+
+    python tests/golden/make_golden.py
+
+What it records (all seeded, fp32 / int64):
+  * roi_align_*.npz — outputs and input-gradients of the reference's own `ROIAlign` module
+    (`detectron2/layers/roi_align.py`, loaded verbatim by file path) running the installed torchvision
+    CPU op, on small maps with interior, over-hanging, degenerate and empty RoIs.
+  * nms_*.npz       — kept indices of `detectron2/layers/nms.py:19-39` (restated in oracle/torch_ref.py;
+    the file itself needs `detectron2.utils.env`) running the installed torchvision CPU `batched_nms`.
+  * head_*.npz / align_*.npz — outputs of oracle/torch_ref.py (the reference has no test for these
+    pieces: "parity unpinned"); `align_world2.npz` additionally comes from the reference's own
+    `GatherLayer` (`detectron2/modeling/backbone/clipcap/gather.py`, loaded verbatim) under a real
+    2-process gloo group, which pins the gather/backward semantics of `caption_consistency_world`.
+
+The tests never read /root/reference; they read these files.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from cddmsl_b200 import synth  # noqa: E402
+from oracle import torch_ref  # noqa: E402
+
+
+def load_by_path(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def roi_cases():
+    ref = load_by_path("ref_roi_align", "detectron2/layers/roi_align.py")
+    g = synth.generator(11)
+    cases = {}
+    for tag, (n, c, h, w, r, p, sr, aligned, scale) in {
+        "p7_s0": (2, 6, 10, 16, 24, 7, 0, True, 1.0 / 16),
+        "p14_s0": (2, 5, 12, 20, 24, 14, 0, True, 1.0 / 16),
+        "p7_s2": (2, 4, 10, 16, 20, 7, 2, True, 1.0 / 16),
+        "p5_legacy": (1, 3, 9, 11, 12, 5, 0, False, 0.25),
+        "p14_big": (1, 3, 38, 63, 10, 14, 0, True, 1.0 / 16),
+    }.items():
+        img_h, img_w = int(h / scale), int(w / scale)
+        feat = torch.randn(n, c, h, w, generator=g)
+        parts = []
+        per = r // n
+        for i in range(n):
+            b = synth.make_boxes(per, img_h, img_w, g, min_side=4.0, degenerate_frac=0.1)
+            # over-hanging RoIs: shift a few outside the image (negative and beyond the far border)
+            b[0] += torch.tensor([-0.6 * img_w, -0.3 * img_h, -0.2 * img_w, 0.0])
+            b[1] += torch.tensor([0.5 * img_w, 0.4 * img_h, 0.9 * img_w, 0.8 * img_h])
+            b[2] = torch.tensor([0.0, 0.0, float(img_w), float(img_h)])          # whole image
+            b[3] = torch.tensor([3.0 * 4, 4.0 * 4, 5.0 * 4, 4.0 * 4])            # empty (zero height)
+            b[4] = torch.tensor([0.7 * img_w, 0.7 * img_h, 0.4 * img_w, 0.5 * img_h])  # inverted
+            parts.append(torch.cat([torch.full((per, 1), float(i)), b], 1))
+        rois = torch.cat(parts, 0)
+        op = ref.ROIAlign((p, p), scale, sr, aligned=aligned)
+        x = feat.clone().requires_grad_(True)
+        out = op(x, rois)
+        gout = torch.randn(out.shape, generator=g)
+        out.backward(gout)
+        cases[tag] = dict(feat=feat.numpy(), rois=rois.numpy(), out=out.detach().numpy(), gout=gout.numpy(),
+                          gin=x.grad.numpy(), meta=np.array([p, p, sr, int(aligned)], dtype=np.int64),
+                          scale=np.array([scale], dtype=np.float64))
+    for tag, d in cases.items():
+        np.savez_compressed(os.path.join(HERE, f"roi_align_{tag}.npz"), **d)
+    print("roi_align:", list(cases))
+
+
+def nms_cases():
+    g = synth.generator(12)
+    out = {}
+    for tag, (m, k, thrs, hw) in {
+        "c1_m300": (300, 1, (0.2, 0.5, 0.7, 0.8), (200, 300)),
+        "c7_m600_trick": (600, 7, (0.2, 0.5, 0.8), (200, 300)),     # numel 2400 <= 4000 -> coordinate trick
+        "c5_m1500_vanilla": (1500, 5, (0.3, 0.7), (300, 400)),      # numel 6000 > 4000 -> per-class loop
+        "rpn_m3000": (3000, 1, (0.7,), (600, 1000)),
+    }.items():
+        boxes, scores, idxs = synth.make_nms_inputs(m, hw[0], hw[1], g, num_classes=k, tie_frac=0.05)
+        d = dict(boxes=boxes.numpy(), scores=scores.numpy(), idxs=idxs.numpy(),
+                 thrs=np.array(thrs, dtype=np.float64))
+        for t in thrs:
+            d[f"keep_{t}"] = torch_ref.batched_nms(boxes, scores, idxs, t).numpy()
+        out[tag] = d
+    # reference test_nms.py:16-29 shape: random_boxes(2000, 200), 50 classes
+    torch.manual_seed(121)
+    n = 2000
+    b = torch.rand(n, 4) * 100
+    b.clamp_(min=1.0)
+    b[:, 2:] += b[:, :2]
+    s = torch.rand(n)
+    ids = torch.randint(0, 50, (n,))
+    d = dict(boxes=b.numpy(), scores=s.numpy(), idxs=ids.numpy(), thrs=np.array([0.2, 0.5, 0.8]))
+    for t in (0.2, 0.5, 0.8):
+        d[f"keep_{t}"] = torch_ref.batched_nms(b, s, ids, t).numpy()
+    out["ref_test_n2000_c50"] = d
+    for tag, d in out.items():
+        np.savez_compressed(os.path.join(HERE, f"nms_{tag}.npz"), **d)
+    print("nms:", list(out))
+
+
+def head_cases():
+    g = synth.generator(13)
+    cfg = synth.CONFIGS["tiny"]
+    r = 96
+    x, w, w_bg, gt = synth.make_head_inputs(cfg, g, n_rois=r)
+    w_bg2 = torch.randn(1, cfg.emb_dim, generator=g) * 0.1   # a checkpoint may overwrite the zero bg row
+    d = dict(x=x.numpy(), w=w.numpy(), gt=gt.numpy(), w_bg2=w_bg2.numpy(),
+             params=np.array([cfg.temperature, cfg.focal_gamma, cfg.bg_weight], dtype=np.float64))
+    for tag, wb in (("zero_bg", w_bg), ("learned_bg", w_bg2)):
+        xx = x.clone().requires_grad_(True)
+        scores = torch_ref.clip_head_scores(xx, w, wb, cfg.temperature)
+        loss = torch_ref.focal_loss(scores, gt, cfg.num_classes, cfg.focal_gamma, cfg.bg_weight)
+        loss.backward()
+        d[f"scores_{tag}"] = scores.detach().numpy()
+        d[f"loss_{tag}"] = loss.detach().numpy()
+        d[f"dx_{tag}"] = xx.grad.numpy()
+        d[f"stats_{tag}"] = np.array(torch_ref.classification_stats(scores.detach(), gt), dtype=np.int64)
+        for lt, (gam, bw) in {"ce": (None, None), "wce": (None, cfg.bg_weight)}.items():
+            xx = x.clone().requires_grad_(True)
+            sc = torch_ref.clip_head_scores(xx, w, wb, cfg.temperature)
+            ls = torch_ref.cls_loss(sc, gt, cfg.num_classes, gam, bw)
+            ls.backward()
+            d[f"loss_{lt}_{tag}"] = ls.detach().numpy()
+            d[f"dx_{lt}_{tag}"] = xx.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "head_tiny.npz"), **d)
+    print("head: tiny")
+
+
+def _gather_worker(rank, world, a_locals, b_locals, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = "29591"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gl = load_by_path("ref_gather", "detectron2/modeling/backbone/clipcap/gather.py")
+    a = a_locals[rank].clone().requires_grad_(True)
+    b = b_locals[rank].clone().requires_grad_(True)
+    a_all = torch.cat(gl.GatherLayer.apply(a), dim=0)      # rcnn.py:455-456
+    b_all = torch.cat(gl.GatherLayer.apply(b), dim=0)
+    loss = torch_ref.caption_consistency_loss(a_all, b_all)  # rcnn.py:458-468
+    loss.backward()
+    q.put((rank, loss.detach().numpy(), a.grad.numpy(), b.grad.numpy()))
+    dist.destroy_process_group()
+
+
+def align_cases():
+    import torch.multiprocessing as mp
+
+    g = synth.generator(14)
+    d = {}
+    for tag, (n, dim) in {"n16": (16, 256), "n40": (40, 64), "n256": (256, 256)}.items():
+        a, b = torch.randn(n, dim, generator=g), torch.randn(n, dim, generator=g)
+        aa, bb = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        loss = torch_ref.caption_consistency_loss(aa, bb)
+        loss.backward()
+        d.update({f"a_{tag}": a.numpy(), f"b_{tag}": b.numpy(), f"loss_{tag}": loss.detach().numpy(),
+                  f"da_{tag}": aa.grad.numpy(), f"db_{tag}": bb.grad.numpy()})
+    np.savez_compressed(os.path.join(HERE, "align_single.npz"), **d)
+
+    world, n_l, dim = 2, 12, 64
+    a_locals = [torch.randn(n_l, dim, generator=g) for _ in range(world)]
+    b_locals = [torch.randn(n_l, dim, generator=g) for _ in range(world)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, a_locals, b_locals, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    [p.join() for p in procs]
+    emu_loss, emu_ga, emu_gb = torch_ref.caption_consistency_world(a_locals, b_locals)
+    for r in range(world):   # the emulation must agree with the real GatherLayer before it is recorded
+        assert np.allclose(res[r][1], emu_loss.numpy(), rtol=1e-6, atol=1e-7)
+        assert np.allclose(res[r][2], emu_ga[r].numpy(), rtol=1e-5, atol=1e-8)
+        assert np.allclose(res[r][3], emu_gb[r].numpy(), rtol=1e-5, atol=1e-8)
+    w = {"loss": res[0][1]}
+    for r in range(world):
+        w.update({f"a{r}": a_locals[r].numpy(), f"b{r}": b_locals[r].numpy(), f"da{r}": res[r][2],
+                  f"db{r}": res[r][3]})
+    np.savez_compressed(os.path.join(HERE, "align_world2.npz"), **w)
+    print("align: single + world2 (real GatherLayer under gloo agrees with the emulation)")
+
+
+if __name__ == "__main__":
+    assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
+    roi_cases()
+    nms_cases()
+    head_cases()
+    align_cases()
+    sizes = {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")}
+    print(sizes, sum(sizes.values()))
