@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — RoIs/s of CDDMSL's region-level hot path (ROIAlign fwd+bwd, CLIP region-text head fwd+bwd,
+caption-consistency alignment loss fwd+bwd) on N B200s; BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload voc|city]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input (per GPU: 16 images, 512 RoIs per
+image).  `value` is timed with the inputs resident in HBM through the C-ABI-backed ops; `e2e` runs the same
+work through the reference-shaped public API (ROIAlign / FastRCNNOutputLayers / caption_consistency_loss +
+autograd) with pinned-host inputs copied in and results copied out every step.  `--impl reference` times the
+reference's CPU path (oracle/torch_ref.py: torchvision CPU ops + ATen, all host threads) on a bounded sample.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cddmsl_b200 import synth  # noqa: E402
+
+METRIC = "RoIs/sec (ROIAlign+CLIP region-text head fwd+bwd)"
+UNIT = "RoIs/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="voc", choices=["voc", "city", "tiny"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--tune", action="append", default=[], help="key=value for cddmsl_tune (kernel sweeps)")
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step(cfg, sample_images: int, sample_rpi: int, seed: int):
+    """One pass of the reference's CPU path on a bounded sample; returns (seconds, n_rois)."""
+    from oracle import torch_ref
+
+    g = synth.generator(seed)
+    feat = synth.make_features(cfg, g, n_images=sample_images).requires_grad_(True)
+    rois = synth.make_rois(cfg, g, n_images=sample_images, rois_per_image=sample_rpi)
+    r = rois.shape[0]
+    x, w, w_bg, gt = synth.make_head_inputs(cfg, g, n_rois=r)
+    x.requires_grad_(True)
+    i_s, i_t, r_s, r_t = [t.requires_grad_(True) for t in synth.make_align_inputs(cfg, g, n_images=sample_images)]
+    t0 = time.perf_counter()
+    out = torch_ref.roi_align(feat, rois, (cfg.pooled, cfg.pooled), 1.0 / cfg.stride, cfg.sampling_ratio, True)
+    scores = torch_ref.clip_head_scores(x, w, w_bg, cfg.temperature)
+    loss_cls = torch_ref.focal_loss(scores, gt, cfg.num_classes, cfg.focal_gamma, cfg.bg_weight)
+    l_img = torch_ref.caption_consistency_loss(i_t, i_s)
+    l_reg = torch_ref.caption_consistency_loss(r_s, r_t)
+    torch.autograd.backward([out, loss_cls, l_img, l_reg],
+                            [out.detach(), torch.ones(()), torch.ones(()), torch.ones(())])
+    dt = time.perf_counter() - t0
+    return dt, r
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = synth.CONFIGS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_img, rpi = 2, 64
+    for i in range(args.warmup):
+        cpu_reference_step(cfg, n_img, rpi, 10 + i)
+    t, rois = 0.0, 0
+    for i in range(args.steps):
+        dt, r = cpu_reference_step(cfg, n_img, rpi, 100 + i)
+        t += dt
+        rois += r
+    v = rois / t
+    sample = (f"{n_img} images x {rpi} RoIs of the '{cfg.name}' workload per step ({cfg.feat_hw[0]}x{cfg.feat_hw[1]} map, "
+              f"{cfg.channels} ch, 14x14, K={cfg.num_classes}) + alignment losses; torchvision CPU ops + ATen "
+              f"(oracle/torch_ref.py), {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, n_gpus):
+    return {"workload": f"{cfg.name}: per GPU {cfg.n_images} images {cfg.img_h}x{cfg.img_w} -> res4 "
+                        f"{cfg.channels}x{cfg.feat_hw[0]}x{cfg.feat_hw[1]}, {cfg.rois_per_image} RoIs/img, "
+                        f"ROIAlign 14x14 s=0 aligned, {cfg.num_classes}-concept CLIP head + bg (T=0.01, focal 0.5, "
+                        f"bg 0.2), caption-consistency loss image-level n={cfg.n_images}/GPU and region-level "
+                        f"n={cfg.n_images * cfg.regions_per_image}/GPU (256-d), fwd+bwd",
+            "rois_per_gpu": cfg.n_rois, "global_rois": cfg.n_rois * n_gpus, "parallelism": f"dp{n_gpus} (by image)",
+            "l2_policy": "inputs larger than L2 (6.6 GB pooled tensor, 157 MB feature map per step)"}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from cddmsl_b200 import _lib, ops
+    from cddmsl_b200.layers import ROIAlign
+    from cddmsl_b200.modeling import (Box2BoxTransform, FastRCNNOutputLayers, caption_consistency_loss,
+                                      image_caption_consistency_loss)
+    from cddmsl_b200.structures import Boxes, Instances
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        assert _lib.tune(k, int(v)), f"unknown tuning key {k}"
+
+    cfg = synth.CONFIGS[args.workload]
+    g = synth.generator(cfg.seed + 1000 * rank)
+    P, scale = cfg.pooled, 1.0 / cfg.stride
+    h_feat = synth.make_features(cfg, g).pin_memory()
+    h_rois = synth.make_rois(cfg, g).pin_memory()
+    hx, hw, hwbg, hgt = synth.make_head_inputs(cfg, g)
+    hx, hgt = hx.pin_memory(), hgt.pin_memory()
+    h_align = [t.pin_memory() for t in synth.make_align_inputs(cfg, g)]
+    R, N, C = cfg.n_rois, cfg.n_images, cfg.channels
+    Hf, Wf = cfg.feat_hw
+
+    feat, rois, x, gt = h_feat.to(dev), h_rois.to(dev), hx.to(dev), hgt.to(dev)
+    w, w_bg = hw.to(dev), hwbg.to(dev)
+    a_is, a_it, a_rs, a_rt = [t.to(dev) for t in h_align]
+    one = torch.ones(1, device=dev)
+
+    def align_fused(a, b):
+        packed, norms = ops.align_pack(a, b)
+        if world > 1:
+            allp = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
+            dist.all_gather_into_tensor(allp, packed)
+        else:
+            allp = packed.unsqueeze(0)
+        return ops.align_loss(allp, norms, rank, one, True)
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+
+    def device_step(i=None):
+        e = ev[i] if i is not None else None
+        if e: e[0].record()
+        out = ops.roi_align(feat, rois, scale, P, P, cfg.sampling_ratio, True)
+        if e: e[1].record()
+        loss, _, dx, stats = ops.clip_head_loss(x, w, w_bg, gt, cfg.temperature, ops.LOSS_FOCAL, cfg.focal_gamma,
+                                                cfg.bg_weight, one, False, False, True)
+        if e: e[2].record()
+        l_img = align_fused(a_it, a_is)
+        l_reg = align_fused(a_rs, a_rt)
+        if e: e[3].record()
+        gin = ops.roi_align_backward(out, rois, scale, P, P, N, C, Hf, Wf, cfg.sampling_ratio, True)
+        if e: e[4].record()
+        return loss, l_img[0], l_reg[0], gin, dx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        res = device_step(i)
+    t1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    seg = [statistics.mean(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)) for j in range(4)]
+    losses = [float(v) for v in res[:3]]
+
+    # ---------------- end to end through the reference-shaped API, host buffers in and out every step
+    e2e = None
+    if not args.no_e2e:
+        pooler = ROIAlign((P, P), scale, cfg.sampling_ratio, aligned=True)
+        head = FastRCNNOutputLayers(cfg.emb_dim, box2box_transform=Box2BoxTransform((10.0, 10.0, 5.0, 5.0)),
+                                    num_classes=cfg.num_classes, clip_cls_emb=(True, hw, "CLIPRes5ROIHeads", cfg.emb_dim),
+                                    bg_cls_loss_weight=cfg.bg_weight,
+                                    openset_test=(None, None, cfg.temperature, cfg.focal_gamma)).to(dev).train()
+        head.bbox_pred.requires_grad_(False)
+        o_gin = torch.empty_like(h_feat).pin_memory()
+        o_dx = torch.empty_like(hx).pin_memory()
+        o_ga = [torch.empty_like(t).pin_memory() for t in h_align]
+        o_sc = torch.empty(4).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in [h_feat, h_rois, hx, hgt] + h_align)
+        d2h = sum(t.numel() * t.element_size() for t in [o_gin, o_dx, o_sc] + o_ga)
+
+        def e2e_step():
+            f = h_feat.to(dev, non_blocking=True).requires_grad_(True)
+            r = h_rois.to(dev, non_blocking=True)
+            xx = hx.to(dev, non_blocking=True).requires_grad_(True)
+            gg = hgt.to(dev, non_blocking=True)
+            al = [t.to(dev, non_blocking=True).requires_grad_(True) for t in h_align]
+            out = pooler(f, r)
+            inst = Instances((cfg.img_h, cfg.img_w))
+            inst.proposal_boxes = Boxes(r[:, 1:])
+            inst.gt_classes = gg
+            scores, deltas = head(xx)
+            lc = head.losses((scores, deltas.detach()), [inst])["loss_cls"]
+            li = image_caption_consistency_loss(al[1], al[0])
+            lr = caption_consistency_loss(al[2], al[3])
+            torch.autograd.backward([out, lc, li, lr], [out.detach(), one[0], one[0], one[0]])
+            o_gin.copy_(f.grad, non_blocking=True)
+            o_dx.copy_(xx.grad, non_blocking=True)
+            for o, t in zip(o_ga, al):
+                o.copy_(t.grad, non_blocking=True)
+            o_sc.copy_(torch.stack([lc.detach(), li.detach(), lr.detach(), lc.detach() * 0]), non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        k2 = max(3, args.steps // 2)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(k2):
+            e2e_step()
+        s1.record()
+        barrier()
+        ms2 = s0.elapsed_time(s1)
+        if world > 1:
+            tt = torch.tensor([ms2], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms2 = float(tt.item())
+        e2e = {"value": world * R * k2 / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms2 / k2, "steps": k2,
+               "api": "ROIAlign.forward + FastRCNNOutputLayers.forward/losses + caption_consistency_loss + autograd"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (ROIAlign fwd or bwd), algorithmic bytes / CUDA-event time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    bytes_roi = R * (4 * C * P * P + 20) + N * C * Hf * Wf * 4
+    names = ["roi_align_fwd", "clip_head_fwd_bwd", "align_loss_x2_fwd_bwd", "roi_align_bwd"]
+    kern = {n: {"ms": round(seg[j], 4)} for j, n in enumerate(names)}
+    kern["roi_align_fwd"].update(gbs=bytes_roi / (seg[0] * 1e-3) / 1e9, bytes=bytes_roi)
+    kern["roi_align_bwd"].update(gbs=bytes_roi / (seg[3] * 1e-3) / 1e9, bytes=bytes_roi)
+    head_bytes = R * (2 * cfg.emb_dim * 4 + 8)
+    kern["clip_head_fwd_bwd"].update(gbs=head_bytes / (seg[1] * 1e-3) / 1e9, bytes=head_bytes)
+    dom = "roi_align_bwd" if seg[3] >= seg[0] else "roi_align_fwd"
+    ach = kern[dom]["gbs"]
+    step_bytes = 2 * bytes_roi + head_bytes
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "step_frac": (step_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
+                "step_algorithmic_bytes": step_bytes}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ref = synth.CONFIGS["cpu_ref"]
+        cpu_reference_step(ref, 1, 32, 1)  # warm-up
+        dt, r = cpu_reference_step(ref, ref.n_images, ref.rois_per_image, ref.seed)
+        cpu_baseline = {"value": r / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+                        "sample": "BASELINE.json configs[0]: 2 images x 512 RoIs (38x63 map, 1024 ch, 14x14, K=20) "
+                                  "fwd+bwd once, torchvision CPU ops + ATen via oracle/torch_ref.py, all host threads"}
+
+    line = {"metric": METRIC, "value": world * R * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kern,
+            "losses": {"loss_cls": losses[0], "align_image": losses[1], "align_region": losses[2]}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
