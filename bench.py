@@ -277,7 +277,7 @@ def run_ours(args):
             al = [t.to(dev, non_blocking=True).requires_grad_(True) for t in h_align]
             out = pooler(f, r)
             inst = Instances((cfg.img_h, cfg.img_w))
-            inst.proposal_boxes = Boxes(r[:, 1:])
+            inst.proposal_boxes = Boxes(r[:, 1:] + r.new_tensor([0.0, 0.0, 1.0, 1.0]))  # box-reg branch wants w,h > 0
             inst.gt_classes = gg
             scores, deltas = head(xx)
             lc = head.losses((scores, deltas.detach()), [inst])["loss_cls"]

@@ -275,7 +275,8 @@ class FastRCNNOutputLayers(nn.Module):
 
     def losses(self, predictions, proposals):
         scores, proposal_deltas = predictions
-        gt_classes = cat([p.gt_classes for p in proposals], dim=0) if len(proposals) else torch.empty(0)
+        gt_classes = (cat([p.gt_classes for p in proposals], dim=0) if len(proposals)
+                      else torch.empty(0, dtype=torch.int64, device=scores.device))  # upstream: float empty(0)
         if len(proposals):
             proposal_boxes = cat([p.proposal_boxes.tensor for p in proposals], dim=0)
             assert not proposal_boxes.requires_grad, "Proposals should not require gradients!"
