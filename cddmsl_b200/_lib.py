@@ -23,7 +23,8 @@ SIGNATURES = {
     "cddmsl_abi_version": (_i, []),
     "cddmsl_error_string": (ctypes.c_char_p, [_i]),
     "cddmsl_launch_count": (ctypes.c_uint64, []),
-    "cddmsl_roi_align_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "cddmsl_roi_align_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "cddmsl_roi_align_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     "cddmsl_roi_align_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "cddmsl_roi_align_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     "cddmsl_nms_workspace_bytes": (_sz, [_i64]),

@@ -1,0 +1,465 @@
+// ROIAlign forward / backward, channels-last formulation (the fast path for the 14x14 pooler of the
+// reference's configs: config/defaults.py:423-426).
+//
+// Why: the first version of these kernels (roi_align.cu, kept as the generic path) turned out to be
+// instruction-issue bound (ncu: 73-81 % issue-active, 4-11 warp instructions per element) because with an NCHW
+// map the lanes of a warp must be spread over bins, so every lane needs its own taps, its own addresses and a
+// staged copy of the footprint.  With the 32 lanes of a warp on 32 CHANNELS instead:
+//   * a bilinear tap is one fully coalesced 128-byte load from a channels-last copy of the map — no staging,
+//   * taps, weights and all control flow are warp-uniform (read from a tiny per-RoI table in shared memory),
+//   * a warp owns two output rows (ph, ph+1) of 32 channels and walks the footprint columns once with a
+//     register sliding window (separable form out = Ay F Ax^T: vertical blend per column, reused by every
+//     sample that touches the column),
+//   * the 2x14 results per lane are 28 contiguous floats of the [R,C,14,14] output: seven conflict-free
+//     STS.128 into the CTA's output tile, which leaves as ONE TMA bulk store (full 128-byte lines).
+// The NCHW <-> NHWC copies of the feature / gradient map are 2 x 157 MB against 6.6 GB of pooled tensor.
+// The backward is the exact transpose: the grad tile comes in through shared memory, the window accumulates
+// T = G Ax per column and flushes dF[y][x][32ch] += Ay^T T with coalesced 128-byte red.global.add.f32.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "roi_common.cuh"
+
+namespace cddmsl {
+
+constexpr int kMaxG = 16;  // samples per bin and axis that fit the tap tables (RoIs up to 224 cells)
+
+struct __align__(16) TapE {
+  int lo;    // absolute column / row index of the low tap, -1: sample contributes nothing
+  int hi;
+  float wl;  // weights (x table: already divided by the sample count)
+  float wh;
+};
+
+// ------------------------------------------------------------------------------------------------
+// [N][A][B] -> [N][B][A] tiled transpose (NCHW <-> NHWC with A=C,B=H*W or the reverse)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int A,
+                                                        int B) {
+  __shared__ float tile[32][33];
+  const size_t img = (size_t)blockIdx.z * A * B;
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int a = a0 + ty + k, b = b0 + tx;
+    if (a < A && b < B) tile[ty + k][tx] = __ldg(in + img + (size_t)a * B + b);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int b = b0 + ty + k, a = a0 + tx;
+    if (a < A && b < B) out[img + (size_t)b * A + a] = tile[tx][ty + k];
+  }
+}
+
+int launch_transpose(const float* in, float* out, int N, int A, int B, cudaStream_t stream) {
+  if (N == 0 || A == 0 || B == 0) return 0;
+  dim3 grid(ceil_div(B, 32), ceil_div(A, 32), N);
+  transpose_kernel<<<grid, 256, 0, stream>>>(in, out, A, B);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared prologue: per-RoI tap tables
+// ------------------------------------------------------------------------------------------------
+template <int P, int NT>
+__device__ __forceinline__ void build_tables(TapE* xtab, TapE* ytab, const RoiGeom& g, int H, int W) {
+  for (int t = threadIdx.x; t < P * g.gw; t += NT) {
+    const int p = t / g.gw, i = t - p * g.gw;
+    const Tap tp = make_tap(g.sw, g.bw, p, i, g.gw, W, 0);
+    TapE e;
+    e.lo = (tp.wl == 0.f && tp.wh == 0.f) ? -1 : tp.lo;
+    e.hi = tp.hi;
+    e.wl = tp.wl * g.inv_count;
+    e.wh = tp.wh * g.inv_count;
+    xtab[t] = e;
+  }
+  for (int t = threadIdx.x; t < P * g.gh; t += NT) {
+    const int p = t / g.gh, i = t - p * g.gh;
+    const Tap tp = make_tap(g.sh, g.bh, p, i, g.gh, H, 0);
+    TapE e;
+    e.lo = (tp.wl == 0.f && tp.wh == 0.f) ? -1 : tp.lo;
+    e.hi = tp.hi;
+    e.wl = tp.wl;
+    e.wh = tp.wh;
+    ytab[t] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+// Vertical blend of one footprint column for the warp's two rows: v = sum_i wl_i F[lo_i][x] + wh_i F[hi_i][x].
+template <int GH>
+struct RowTaps {  // GH > 0: taps in registers;  GH == 0: read from the table every time
+  int olo[GH > 0 ? GH : 1], ohi[GH > 0 ? GH : 1];
+  float wl[GH > 0 ? GH : 1], wh[GH > 0 ? GH : 1];
+};
+
+template <int GH>
+__device__ __forceinline__ void load_row_taps(RowTaps<GH>& rt, const TapE* ytab_row, int WC) {
+#pragma unroll
+  for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {
+    const TapE e = ytab_row[i];
+    const bool ok = e.lo >= 0;
+    rt.olo[i] = ok ? e.lo * WC : 0;
+    rt.ohi[i] = ok ? e.hi * WC : 0;
+    rt.wl[i] = ok ? e.wl : 0.f;
+    rt.wh[i] = ok ? e.wh : 0.f;
+  }
+}
+
+template <int GH>
+__device__ __forceinline__ void fwd_column(const float* __restrict__ col, const RowTaps<GH>& ra, const RowTaps<GH>& rb,
+                                           const TapE* ya, const TapE* yb, int gh, int WC, float& va, float& vb) {
+  if (GH > 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {
+      a = fmaf(ra.wl[i], __ldg(col + ra.olo[i]), a);
+      a = fmaf(ra.wh[i], __ldg(col + ra.ohi[i]), a);
+      b = fmaf(rb.wl[i], __ldg(col + rb.olo[i]), b);
+      b = fmaf(rb.wh[i], __ldg(col + rb.ohi[i]), b);
+    }
+    va = a;
+    vb = b;
+  } else {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < gh; ++i) {
+      const TapE ea = ya[i], eb = yb[i];
+      if (ea.lo >= 0) {
+        a = fmaf(ea.wl, __ldg(col + ea.lo * WC), a);
+        a = fmaf(ea.wh, __ldg(col + ea.hi * WC), a);
+      }
+      if (eb.lo >= 0) {
+        b = fmaf(eb.wl, __ldg(col + eb.lo * WC), b);
+        b = fmaf(eb.wh, __ldg(col + eb.hi * WC), b);
+      }
+    }
+    va = a;
+    vb = b;
+  }
+}
+
+template <int P, int GH>
+__device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image + channel of this lane */,
+                                         const TapE* __restrict__ xtab, const TapE* __restrict__ ytab, int gw, int gh,
+                                         int W, int C, int row_a, float* __restrict__ orow) {
+  const int WC = W * C;
+  RowTaps<GH> ra, rb;
+  const TapE* ya = ytab + row_a * gh;
+  const TapE* yb = ya + gh;
+  load_row_taps<GH>(ra, ya, WC);
+  load_row_taps<GH>(rb, yb, WC);
+  float oa[P], ob[P];
+  int cur = -4;
+  float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
+#pragma unroll
+  for (int pw = 0; pw < P; ++pw) {
+    float sa = 0.f, sb = 0.f;
+    const TapE* xt = xtab + pw * gw;
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      if (e.lo < 0) continue;  // outside [-1, W]: contributes nothing (warp-uniform)
+      if (e.lo != cur) {
+        if (e.lo == cur + 1) {
+          va0 = va1;
+          vb0 = vb1;
+        } else {
+          fwd_column<GH>(base + (size_t)e.lo * C, ra, rb, ya, yb, gh, WC, va0, vb0);
+        }
+        cur = e.lo;
+        if (cur + 1 < W) {
+          fwd_column<GH>(base + (size_t)(cur + 1) * C, ra, rb, ya, yb, gh, WC, va1, vb1);
+        } else {
+          va1 = vb1 = 0.f;
+        }
+      }
+      sa = fmaf(e.wl, va0, sa);
+      sa = fmaf(e.wh, va1, sa);
+      sb = fmaf(e.wl, vb0, sb);
+      sb = fmaf(e.wh, vb1, sb);
+    }
+    oa[pw] = sa;
+    ob[pw] = sb;
+  }
+  // 2*P contiguous floats of the output tile: rows a and b of this lane's channel
+  float4* o4 = reinterpret_cast<float4*>(orow);
+#pragma unroll
+  for (int k = 0; k < (2 * P) / 4; ++k) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = 4 * k + q;
+      v[q] = idx < P ? oa[idx < P ? idx : 0] : ob[idx >= P ? idx - P : 0];
+    }
+    o4[k] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+__device__ void fwd_direct_any(const float* __restrict__ in, float* __restrict__ out_roi, int c0, int nch, int C, int H,
+                               int W, int PH, int PW, const RoiGeom& g, int nthreads) {
+  const int per = PH * PW;
+  for (int e = threadIdx.x; e < nch * per; e += nthreads) {
+    const int c = e / per, b = e - c * per;
+    const int ph = b / PW, pw = b - ph * PW;
+    const float* plane = in + ((size_t)g.batch * C + c0 + c) * H * W;
+    float acc = 0.f;
+    for (int iy = 0; iy < g.gh; ++iy) {
+      const Tap ty = make_tap(g.sh, g.bh, ph, iy, g.gh, H, 0);
+      for (int ix = 0; ix < g.gw; ++ix) {
+        const Tap tx = make_tap(g.sw, g.bw, pw, ix, g.gw, W, 0);
+        acc += ty.wl * tx.wl * plane[ty.lo * W + tx.lo] + ty.wl * tx.wh * plane[ty.lo * W + tx.hi] +
+               ty.wh * tx.wl * plane[ty.hi * W + tx.lo] + ty.wh * tx.wh * plane[ty.hi * W + tx.hi];
+      }
+    }
+    out_roi[(size_t)(c0 + c) * per + b] = acc * g.inv_count;
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__((P / 2) * 32, 3)
+roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ in_nchw,
+                        const float* __restrict__ rois, float* __restrict__ out, int N, int C, int H, int W, int R,
+                        float scale, int sampling_ratio, int aligned, int ngroups) {
+  constexpr int NW = P / 2, NT = NW * 32, PER = P * P;
+  __shared__ __align__(128) float O_s[32 * PER];
+  __shared__ TapE xtab[P * kMaxG];
+  __shared__ TapE ytab[P * kMaxG];
+  const int r = blockIdx.x / ngroups;
+  const int c0 = (blockIdx.x - r * ngroups) * 32;
+  const int nc = min(32, C - c0);
+  const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
+  float* out_tile = out + ((size_t)r * C + c0) * PER;
+  if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) {
+    for (int e = threadIdx.x; e < nc * PER; e += NT) out_tile[e] = 0.f;
+    return;
+  }
+  if (g.gw > kMaxG || g.gh > kMaxG) {  // more samples per bin than the tables hold: reference-order loop
+    fwd_direct_any(in_nchw, out + (size_t)r * C * PER, c0, nc, C, H, W, P, P, g, NT);
+    return;
+  }
+  build_tables<P, NT>(xtab, ytab, g, H, W);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cl = min(lane, nc - 1);  // ragged last group: surplus lanes recompute channel nc-1, never stored
+  const float* base = ft + (size_t)g.batch * H * W * C + c0 + cl;
+  float* orow = O_s + cl * PER + (2 * warp) * P;
+  if (lane < nc) {
+    if (g.gh == 1) fwd_rows<P, 1>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow);
+    else if (g.gh == 2) fwd_rows<P, 2>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow);
+    else fwd_rows<P, 0>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(O_s);
+    const uint32_t bytes = (uint32_t)(nc * PER) * 4u;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_tile), "r"(s), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct YSlots {  // up to 4 distinct rows touched by (sample i of row a, sample i of row b), merged
+  int off[4];    // y * W * C, -1: inactive
+  float wa[4], wb[4];
+};
+
+__device__ __forceinline__ YSlots make_slots(const TapE ea, const TapE eb, int WC) {
+  YSlots s;
+  const int y0 = ea.lo >= 0 ? ea.lo : -10, y1 = ea.lo >= 0 ? ea.hi : -11;
+  const int y2 = eb.lo >= 0 ? eb.lo : -12, y3 = eb.lo >= 0 ? eb.hi : -13;
+  const float a0 = ea.lo >= 0 ? ea.wl : 0.f, a1 = ea.lo >= 0 ? ea.wh : 0.f;
+  const float b2 = eb.lo >= 0 ? eb.wl : 0.f, b3 = eb.lo >= 0 ? eb.wh : 0.f;
+  s.off[0] = y0 >= 0 ? y0 * WC : -1;
+  s.wa[0] = a0 + (y1 == y0 ? a1 : 0.f);
+  s.wb[0] = (y2 == y0 ? b2 : 0.f) + (y3 == y0 ? b3 : 0.f);
+  const bool n1 = y1 >= 0 && y1 != y0;
+  s.off[1] = n1 ? y1 * WC : -1;
+  s.wa[1] = a1;
+  s.wb[1] = (y2 == y1 ? b2 : 0.f) + (y3 == y1 ? b3 : 0.f);
+  const bool n2 = y2 >= 0 && y2 != y0 && y2 != y1;
+  s.off[2] = n2 ? y2 * WC : -1;
+  s.wa[2] = 0.f;
+  s.wb[2] = b2 + (y3 == y2 ? b3 : 0.f);
+  const bool n3 = y3 >= 0 && y3 != y0 && y3 != y1 && y3 != y2;
+  s.off[3] = n3 ? y3 * WC : -1;
+  s.wa[3] = 0.f;
+  s.wb[3] = b3;
+  return s;
+}
+
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// dF[y][x][c] += Ay^T (ta, tb) for one footprint column
+template <bool GH1>
+__device__ __forceinline__ void bwd_flush(float* __restrict__ col, const YSlots& s1, const TapE* ya, const TapE* yb,
+                                          int gh, int WC, float ta, float tb) {
+  if (GH1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (s1.off[k] >= 0) red_add(col + s1.off[k], fmaf(s1.wa[k], ta, s1.wb[k] * tb));
+  } else {
+    for (int i = 0; i < gh; ++i) {
+      const YSlots s = make_slots(ya[i], yb[i], WC);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (s.off[k] >= 0) red_add(col + s.off[k], fmaf(s.wa[k], ta, s.wb[k] * tb));
+    }
+  }
+}
+
+template <int P, bool GH1>
+__device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* __restrict__ xtab,
+                                         const TapE* __restrict__ ytab, int gw, int gh, int W, int C, int row_a,
+                                         const float* __restrict__ grow) {
+  const int WC = W * C;
+  const TapE* ya = ytab + row_a * gh;
+  const TapE* yb = ya + gh;
+  YSlots s1;
+  if (GH1) s1 = make_slots(ya[0], yb[0], WC);
+  float ga[P], gb[P];
+  {
+    const float4* g4 = reinterpret_cast<const float4*>(grow);
+#pragma unroll
+    for (int k = 0; k < (2 * P) / 4; ++k) {
+      const float4 v = g4[k];
+      const float q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int idx = 4 * k + t;
+        if (idx < P) ga[idx < P ? idx : 0] = q[t];
+        else gb[idx >= P ? idx - P : 0] = q[t];
+      }
+    }
+  }
+  int cur = -4;
+  float ta0 = 0.f, ta1 = 0.f, tb0 = 0.f, tb1 = 0.f;
+#pragma unroll
+  for (int pw = 0; pw < P; ++pw) {
+    const TapE* xt = xtab + pw * gw;
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      if (e.lo < 0) continue;
+      if (e.lo != cur) {
+        if (cur >= 0) {
+          bwd_flush<GH1>(base + (size_t)cur * C, s1, ya, yb, gh, WC, ta0, tb0);
+          if (e.lo == cur + 1) {
+            ta0 = ta1;
+            tb0 = tb1;
+          } else {
+            if (cur + 1 < W) bwd_flush<GH1>(base + (size_t)(cur + 1) * C, s1, ya, yb, gh, WC, ta1, tb1);
+            ta0 = tb0 = 0.f;
+          }
+        }
+        ta1 = tb1 = 0.f;
+        cur = e.lo;
+      }
+      ta0 = fmaf(e.wl, ga[pw], ta0);
+      ta1 = fmaf(e.wh, ga[pw], ta1);
+      tb0 = fmaf(e.wl, gb[pw], tb0);
+      tb1 = fmaf(e.wh, gb[pw], tb1);
+    }
+  }
+  if (cur >= 0) {
+    bwd_flush<GH1>(base + (size_t)cur * C, s1, ya, yb, gh, WC, ta0, tb0);
+    if (cur + 1 < W) bwd_flush<GH1>(base + (size_t)(cur + 1) * C, s1, ya, yb, gh, WC, ta1, tb1);
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__((P / 2) * 32, 4)
+roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict__ rois, float* __restrict__ gt, int N,
+                        int C, int H, int W, int R, float scale, int sampling_ratio, int aligned, int ngroups) {
+  constexpr int NW = P / 2, NT = NW * 32, PER = P * P;
+  __shared__ __align__(128) float G_s[32 * PER];
+  __shared__ TapE xtab[P * kMaxG];
+  __shared__ TapE ytab[P * kMaxG];
+  const int r = blockIdx.x / ngroups;
+  const int c0 = (blockIdx.x - r * ngroups) * 32;
+  const int nc = min(32, C - c0);
+  const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
+  if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) return;
+  const float* g_tile = gout + ((size_t)r * C + c0) * PER;
+  float* img = gt + (size_t)g.batch * H * W * C + c0;
+  if (g.gw > kMaxG || g.gh > kMaxG) {  // reference-style scatter into the channels-last map
+    for (int e = threadIdx.x; e < nc * PER; e += NT) {
+      const int c = e / PER, b = e - c * PER;
+      const int ph = b / P, pw = b - ph * P;
+      const float go = g_tile[e] * g.inv_count;
+      for (int iy = 0; iy < g.gh; ++iy) {
+        const Tap ty = make_tap(g.sh, g.bh, ph, iy, g.gh, H, 0);
+        if (ty.wl == 0.f && ty.wh == 0.f) continue;
+        for (int ix = 0; ix < g.gw; ++ix) {
+          const Tap tx = make_tap(g.sw, g.bw, pw, ix, g.gw, W, 0);
+          if (tx.wl == 0.f && tx.wh == 0.f) continue;
+          red_add(img + ((size_t)ty.lo * W + tx.lo) * C + c, go * ty.wl * tx.wl);
+          red_add(img + ((size_t)ty.lo * W + tx.hi) * C + c, go * ty.wl * tx.wh);
+          red_add(img + ((size_t)ty.hi * W + tx.lo) * C + c, go * ty.wh * tx.wl);
+          red_add(img + ((size_t)ty.hi * W + tx.hi) * C + c, go * ty.wh * tx.wh);
+        }
+      }
+    }
+    return;
+  }
+  {  // stage the contiguous grad tile (read once, streaming)
+    const float4* s4 = reinterpret_cast<const float4*>(g_tile);
+    float4* d4 = reinterpret_cast<float4*>(G_s);
+    for (int e = threadIdx.x; e < nc * PER / 4; e += NT) d4[e] = __ldcs(s4 + e);
+  }
+  build_tables<P, NT>(xtab, ytab, g, H, W);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane >= nc) return;
+  float* base = img + lane;
+  const float* grow = G_s + lane * PER + (2 * warp) * P;
+  if (g.gh == 1) bwd_rows<P, true>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, grow);
+  else bwd_rows<P, false>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, grow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW) {
+  (void)N;
+  return PH == 14 && PW == 14 && (long long)H * W * C < 0x7fffffffLL;
+}
+
+size_t roi_cl_workspace_bytes(int N, int C, int H, int W) { return align_up((size_t)N * C * H * W * 4, 256); }
+
+int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, float scale,
+                     int sampling_ratio, int aligned, float* ft, cudaStream_t stream) {
+  int rc = launch_transpose(in, ft, N, C, H * W, stream);  // NCHW -> NHWC
+  if (rc) return rc;
+  const int ngroups = ceil_div(C, 32);
+  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
+  roi_align_fwd_cl_kernel<14><<<(unsigned)((long long)R * ngroups), 7 * 32, 0, stream>>>(
+      ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, ngroups);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, float scale,
+                     int sampling_ratio, int aligned, float* gt, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(gt, 0, (size_t)N * C * H * W * sizeof(float), stream);
+  if (e != cudaSuccess) return (int)e;
+  const int ngroups = ceil_div(C, 32);
+  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
+  roi_align_bwd_cl_kernel<14><<<(unsigned)((long long)R * ngroups), 7 * 32, 0, stream>>>(
+      gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, ngroups);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  return launch_transpose(gt, gin, N, H * W, C, stream);  // NHWC -> NCHW (overwrites gin completely)
+}
+
+}  // namespace cddmsl

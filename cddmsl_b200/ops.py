@@ -35,10 +35,12 @@ def roi_align(input: Tensor, rois: Tensor, spatial_scale: float, pooled_height: 
     n, c, h, w = x.shape
     nr = r.shape[0]
     out = torch.empty((nr, c, pooled_height, pooled_width), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_roi_align_fwd_workspace_bytes(n, c, h, w, nr), x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().cddmsl_roi_align_fwd(_lib.ptr(x), _lib.ptr(r), _lib.ptr(out), n, c, h, w, nr,
-                                                   pooled_height, pooled_width, spatial_scale, sampling_ratio,
-                                                   int(aligned), _lib.stream_ptr(x.device)), "roi_align_fwd")
+        _lib.check(L.cddmsl_roi_align_fwd(_lib.ptr(x), _lib.ptr(r), _lib.ptr(out), n, c, h, w, nr, pooled_height,
+                                          pooled_width, spatial_scale, sampling_ratio, int(aligned), _lib.ptr(ws),
+                                          ws.numel(), _lib.stream_ptr(x.device)), "roi_align_fwd")
     return out if input.dtype == torch.float32 else out.to(input.dtype)
 
 

@@ -45,9 +45,12 @@ uint64_t cddmsl_launch_count(void);
 
 /* ---------------------------------------------------------------- piece 1: ROIAlign ------------- */
 /* in [N,C,H,W], rois [R,5] = (batch_idx, x0, y0, x1, y1) in image coordinates, out [R,C,PH,PW]. */
+/* workspace: scratch for the channels-last copy of the map used by the 14x14 fast path; with a NULL / too
+ * small workspace the generic NCHW kernel runs instead (same results, slower). */
+size_t cddmsl_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int R);
 int cddmsl_roi_align_fwd(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R,
-                         int PH, int PW, float spatial_scale, int sampling_ratio, int aligned,
-                         cddmsl_stream_t stream);
+                         int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, void* workspace,
+                         size_t workspace_bytes, cddmsl_stream_t stream);
 
 /* gout [R,C,PH,PW] -> gin [N,C,H,W] (fully overwritten; zeroing happens inside). */
 size_t cddmsl_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R);

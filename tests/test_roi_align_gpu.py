@@ -98,6 +98,24 @@ def test_seeded_random_vs_oracle(p, sr, aligned, c, hw):
     _close(gin, c_ref.roi_align_bwd(gout, rois, feat.shape, 1.0 / 16, sr, aligned), BWD_RTOL)
 
 
+def test_generic_nchw_kernels_on_the_14x14_shape():
+    """The 14x14 pooler normally takes the channels-last fast path; force the generic NCHW kernels (what runs
+    when no workspace is passed through the C ABI) and hold them to the same oracle."""
+    from cddmsl_b200 import _lib
+
+    g = synth.generator(55)
+    feat = torch.randn(2, 48, 38, 63, generator=g).numpy()
+    rois = synth.make_rois(synth.PathConfig("t", 2, 600, 1000, 40, 5), g).numpy()
+    gout = torch.randn(rois.shape[0], 48, 14, 14, generator=g).numpy()
+    assert _lib.tune("roi_use_cl", 0)
+    try:
+        o, gin = _run(feat, rois, (14, 14), 1.0 / 16, 0, True, gout=gout)
+    finally:
+        _lib.tune("roi_use_cl", 1)
+    _close(o, c_ref.roi_align_fwd(feat, rois, (14, 14), 1.0 / 16, 0, True), FWD_RTOL)
+    _close(gin, c_ref.roi_align_bwd(gout, rois, feat.shape, 1.0 / 16, 0, True), BWD_RTOL)
+
+
 def test_rois_in_arbitrary_image_order():
     g = synth.generator(5)
     feat = torch.randn(4, 16, 20, 30, generator=g).numpy()
