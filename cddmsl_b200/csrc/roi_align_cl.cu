@@ -92,41 +92,56 @@ __device__ __forceinline__ void build_tables(TapE* xtab, TapE* ytab, const RoiGe
 // forward
 // ------------------------------------------------------------------------------------------------
 // Vertical blend of one footprint column for the warp's two rows: v = sum_i wl_i F[lo_i][x] + wh_i F[hi_i][x].
+// All addressing is "per-lane 64-bit base + 32-bit element offset" so that one IMAD.WIDE forms each address.
 template <int GH>
-struct RowTaps {  // GH > 0: taps in registers;  GH == 0: read from the table every time
-  int olo[GH > 0 ? GH : 1], ohi[GH > 0 ? GH : 1];
+struct RowTaps {  // GH > 0: row pointers + weights in registers;  GH == 0: read from the table every time
+  const float* plo[GH > 0 ? GH : 1];
+  const float* phi[GH > 0 ? GH : 1];
   float wl[GH > 0 ? GH : 1], wh[GH > 0 ? GH : 1];
 };
 
 template <int GH>
-__device__ __forceinline__ void load_row_taps(RowTaps<GH>& rt, const TapE* ytab_row, int WC) {
+__device__ __forceinline__ void load_row_taps(RowTaps<GH>& rt, const float* __restrict__ base, const TapE* ytab_row,
+                                              int WC) {
 #pragma unroll
   for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {
     const TapE e = ytab_row[i];
     const bool ok = e.lo >= 0;
-    rt.olo[i] = ok ? e.lo * WC : 0;
-    rt.ohi[i] = ok ? e.hi * WC : 0;
+    rt.plo[i] = base + (ok ? e.lo * WC : 0);
+    rt.phi[i] = base + (ok ? e.hi * WC : 0);
     rt.wl[i] = ok ? e.wl : 0.f;
     rt.wh[i] = ok ? e.wh : 0.f;
   }
 }
 
+__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int GH>
-__device__ __forceinline__ void fwd_column(const float* __restrict__ col, const RowTaps<GH>& ra, const RowTaps<GH>& rb,
-                                           const TapE* ya, const TapE* yb, int gh, int WC, float& va, float& vb) {
+__device__ __forceinline__ void fwd_column(const float* __restrict__ base, int xo, const RowTaps<GH>& ra,
+                                           const RowTaps<GH>& rb, const TapE* ya, const TapE* yb, int gh, int WC,
+                                           float& va, float& vb) {
   if (GH > 0) {
+    float l[4 * (GH > 0 ? GH : 1)];
+#pragma unroll
+    for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {  // issue every load of the column before the first use
+      l[4 * i + 0] = __ldg(ra.plo[i] + xo);
+      l[4 * i + 1] = __ldg(ra.phi[i] + xo);
+      l[4 * i + 2] = __ldg(rb.plo[i] + xo);
+      l[4 * i + 3] = __ldg(rb.phi[i] + xo);
+    }
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {
-      a = fmaf(ra.wl[i], __ldg(col + ra.olo[i]), a);
-      a = fmaf(ra.wh[i], __ldg(col + ra.ohi[i]), a);
-      b = fmaf(rb.wl[i], __ldg(col + rb.olo[i]), b);
-      b = fmaf(rb.wh[i], __ldg(col + rb.ohi[i]), b);
+      a = fmaf(ra.wl[i], l[4 * i + 0], a);
+      a = fmaf(ra.wh[i], l[4 * i + 1], a);
+      b = fmaf(rb.wl[i], l[4 * i + 2], b);
+      b = fmaf(rb.wh[i], l[4 * i + 3], b);
     }
     va = a;
     vb = b;
   } else {
     float a = 0.f, b = 0.f;
+    const float* col = base + xo;
     for (int i = 0; i < gh; ++i) {
       const TapE ea = ya[i], eb = yb[i];
       if (ea.lo >= 0) {
@@ -143,6 +158,37 @@ __device__ __forceinline__ void fwd_column(const float* __restrict__ col, const 
   }
 }
 
+// One sample of the sliding window (warp-uniform control flow).  The column loader appears at ONE site (the
+// t-loop runs once when the window just slides, twice when it (re)starts): the first version of this kernel,
+// fully unrolled over the 14 bins, was 21 K SASS instructions and lost 27 % of its issue slots to
+// instruction-cache misses (ncu stall_no_inst).
+#define CDDMSL_FWD_SAMPLE(e, SA, SB)                                              \
+  if ((e).lo >= 0) {                                                              \
+    if ((e).lo != cur) {                                                          \
+      int t = ((e).lo == cur + 1) ? 1 : 0;                                        \
+      if (t) {                                                                    \
+        va0 = va1;                                                                \
+        vb0 = vb1;                                                                \
+      }                                                                           \
+      cur = (e).lo;                                                               \
+      for (; t < 2; ++t) {                                                        \
+        float na = 0.f, nb = 0.f;                                                 \
+        if (cur + t < W) fwd_column<GH>(base, (cur + t) * C, ra, rb, ya, yb, gh, WC, na, nb); \
+        if (t == 0) {                                                             \
+          va0 = na;                                                               \
+          vb0 = nb;                                                               \
+        } else {                                                                  \
+          va1 = na;                                                               \
+          vb1 = nb;                                                               \
+        }                                                                         \
+      }                                                                           \
+    }                                                                             \
+    SA = fmaf((e).wl, va0, SA);                                                   \
+    SA = fmaf((e).wh, va1, SA);                                                   \
+    SB = fmaf((e).wl, vb0, SB);                                                   \
+    SB = fmaf((e).wh, vb1, SB);                                                   \
+  }
+
 template <int P, int GH>
 __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image + channel of this lane */,
                                          const TapE* __restrict__ xtab, const TapE* __restrict__ ytab, int gw, int gh,
@@ -151,51 +197,27 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
   RowTaps<GH> ra, rb;
   const TapE* ya = ytab + row_a * gh;
   const TapE* yb = ya + gh;
-  load_row_taps<GH>(ra, ya, WC);
-  load_row_taps<GH>(rb, yb, WC);
-  float oa[P], ob[P];
+  load_row_taps<GH>(ra, base, ya, WC);
+  load_row_taps<GH>(rb, base, yb, WC);
   int cur = -4;
   float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
-#pragma unroll
-  for (int pw = 0; pw < P; ++pw) {
-    float sa = 0.f, sb = 0.f;
-    const TapE* xt = xtab + pw * gw;
+  const TapE* xt = xtab;
+#pragma unroll 1
+  for (int pw = 0; pw < P; pw += 2) {
+    float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
     for (int ix = 0; ix < gw; ++ix) {
       const TapE e = xt[ix];
-      if (e.lo < 0) continue;  // outside [-1, W]: contributes nothing (warp-uniform)
-      if (e.lo != cur) {
-        if (e.lo == cur + 1) {
-          va0 = va1;
-          vb0 = vb1;
-        } else {
-          fwd_column<GH>(base + (size_t)e.lo * C, ra, rb, ya, yb, gh, WC, va0, vb0);
-        }
-        cur = e.lo;
-        if (cur + 1 < W) {
-          fwd_column<GH>(base + (size_t)(cur + 1) * C, ra, rb, ya, yb, gh, WC, va1, vb1);
-        } else {
-          va1 = vb1 = 0.f;
-        }
-      }
-      sa = fmaf(e.wl, va0, sa);
-      sa = fmaf(e.wh, va1, sa);
-      sb = fmaf(e.wl, vb0, sb);
-      sb = fmaf(e.wh, vb1, sb);
+      CDDMSL_FWD_SAMPLE(e, sa0, sb0)
     }
-    oa[pw] = sa;
-    ob[pw] = sb;
-  }
-  // 2*P contiguous floats of the output tile: rows a and b of this lane's channel
-  float4* o4 = reinterpret_cast<float4*>(orow);
-#pragma unroll
-  for (int k = 0; k < (2 * P) / 4; ++k) {
-    float v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = 4 * k + q;
-      v[q] = idx < P ? oa[idx < P ? idx : 0] : ob[idx >= P ? idx - P : 0];
+    xt += gw;
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      CDDMSL_FWD_SAMPLE(e, sa1, sb1)
     }
-    o4[k] = make_float4(v[0], v[1], v[2], v[3]);
+    xt += gw;
+    // rows a and b of this lane's channel are 2*P contiguous floats of the output tile
+    *reinterpret_cast<float2*>(orow + pw) = make_float2(sa0, sa1);
+    *reinterpret_cast<float2*>(orow + P + pw) = make_float2(sb0, sb1);
   }
 }
 
@@ -220,7 +242,7 @@ __device__ void fwd_direct_any(const float* __restrict__ in, float* __restrict__
 }
 
 template <int P>
-__global__ void __launch_bounds__((P / 2) * 32, 3)
+__global__ void __launch_bounds__((P / 2) * 32, 4)
 roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ in_nchw,
                         const float* __restrict__ rois, float* __restrict__ out, int N, int C, int H, int W, int R,
                         float scale, int sampling_ratio, int aligned, int ngroups) {
@@ -260,14 +282,15 @@ roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_tile), "r"(s), "r"(bytes)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // the CTA may retire once the copy engine has READ the tile; the global writes complete on their own
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-struct YSlots {  // up to 4 distinct rows touched by (sample i of row a, sample i of row b), merged
+struct __align__(16) YSlots {  // up to 4 distinct rows touched by (sample i of row a, sample i of row b), merged
   int off[4];    // y * W * C, -1: inactive
   float wa[4], wb[4];
 };
@@ -302,77 +325,70 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 
 // dF[y][x][c] += Ay^T (ta, tb) for one footprint column
 template <bool GH1>
-__device__ __forceinline__ void bwd_flush(float* __restrict__ col, const YSlots& s1, const TapE* ya, const TapE* yb,
-                                          int gh, int WC, float ta, float tb) {
+__device__ __forceinline__ void bwd_flush(float* __restrict__ base, int xo, const YSlots& s1,
+                                          const YSlots* __restrict__ slots, int gh, float ta, float tb) {
   if (GH1) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (s1.off[k] >= 0) red_add(col + s1.off[k], fmaf(s1.wa[k], ta, s1.wb[k] * tb));
+      if (s1.off[k] >= 0) red_add(base + (s1.off[k] + xo), fmaf(s1.wa[k], ta, s1.wb[k] * tb));
   } else {
     for (int i = 0; i < gh; ++i) {
-      const YSlots s = make_slots(ya[i], yb[i], WC);
+      const YSlots s = slots[i];  // 3 x LDS.128, warp-uniform
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (s.off[k] >= 0) red_add(col + s.off[k], fmaf(s.wa[k], ta, s.wb[k] * tb));
+        if (s.off[k] >= 0) red_add(base + (s.off[k] + xo), fmaf(s.wa[k], ta, s.wb[k] * tb));
     }
   }
 }
 
+#define CDDMSL_BWD_SAMPLE(e, GA, GB)                                                        \
+  if ((e).lo >= 0) {                                                                        \
+    if ((e).lo != cur) {                                                                    \
+      if (cur >= 0) {                                                                       \
+        const bool adj = ((e).lo == cur + 1);                                               \
+        const int nfl = adj ? 1 : 2;                                                        \
+        for (int t = 0; t < nfl; ++t)                                                       \
+          if (cur + t < W)                                                                  \
+            bwd_flush<GH1>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0); \
+        ta0 = adj ? ta1 : 0.f;                                                              \
+        tb0 = adj ? tb1 : 0.f;                                                              \
+      }                                                                                     \
+      ta1 = tb1 = 0.f;                                                                      \
+      cur = (e).lo;                                                                         \
+    }                                                                                       \
+    ta0 = fmaf((e).wl, GA, ta0);                                                            \
+    ta1 = fmaf((e).wh, GA, ta1);                                                            \
+    tb0 = fmaf((e).wl, GB, tb0);                                                            \
+    tb1 = fmaf((e).wh, GB, tb1);                                                            \
+  }
+
 template <int P, bool GH1>
 __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* __restrict__ xtab,
-                                         const TapE* __restrict__ ytab, int gw, int gh, int W, int C, int row_a,
+                                         const YSlots* __restrict__ slots, int gw, int gh, int W, int C,
                                          const float* __restrict__ grow) {
-  const int WC = W * C;
-  const TapE* ya = ytab + row_a * gh;
-  const TapE* yb = ya + gh;
   YSlots s1;
-  if (GH1) s1 = make_slots(ya[0], yb[0], WC);
-  float ga[P], gb[P];
-  {
-    const float4* g4 = reinterpret_cast<const float4*>(grow);
-#pragma unroll
-    for (int k = 0; k < (2 * P) / 4; ++k) {
-      const float4 v = g4[k];
-      const float q[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int idx = 4 * k + t;
-        if (idx < P) ga[idx < P ? idx : 0] = q[t];
-        else gb[idx >= P ? idx - P : 0] = q[t];
-      }
-    }
-  }
+  if (GH1) s1 = slots[0];
   int cur = -4;
   float ta0 = 0.f, ta1 = 0.f, tb0 = 0.f, tb1 = 0.f;
-#pragma unroll
-  for (int pw = 0; pw < P; ++pw) {
-    const TapE* xt = xtab + pw * gw;
+  const TapE* xt = xtab;
+#pragma unroll 1
+  for (int pw = 0; pw < P; pw += 2) {
+    const float2 ga = *reinterpret_cast<const float2*>(grow + pw);
+    const float2 gb = *reinterpret_cast<const float2*>(grow + P + pw);
     for (int ix = 0; ix < gw; ++ix) {
       const TapE e = xt[ix];
-      if (e.lo < 0) continue;
-      if (e.lo != cur) {
-        if (cur >= 0) {
-          bwd_flush<GH1>(base + (size_t)cur * C, s1, ya, yb, gh, WC, ta0, tb0);
-          if (e.lo == cur + 1) {
-            ta0 = ta1;
-            tb0 = tb1;
-          } else {
-            if (cur + 1 < W) bwd_flush<GH1>(base + (size_t)(cur + 1) * C, s1, ya, yb, gh, WC, ta1, tb1);
-            ta0 = tb0 = 0.f;
-          }
-        }
-        ta1 = tb1 = 0.f;
-        cur = e.lo;
-      }
-      ta0 = fmaf(e.wl, ga[pw], ta0);
-      ta1 = fmaf(e.wh, ga[pw], ta1);
-      tb0 = fmaf(e.wl, gb[pw], tb0);
-      tb1 = fmaf(e.wh, gb[pw], tb1);
+      CDDMSL_BWD_SAMPLE(e, ga.x, gb.x)
     }
+    xt += gw;
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      CDDMSL_BWD_SAMPLE(e, ga.y, gb.y)
+    }
+    xt += gw;
   }
   if (cur >= 0) {
-    bwd_flush<GH1>(base + (size_t)cur * C, s1, ya, yb, gh, WC, ta0, tb0);
-    if (cur + 1 < W) bwd_flush<GH1>(base + (size_t)(cur + 1) * C, s1, ya, yb, gh, WC, ta1, tb1);
+    for (int t = 0; t < 2; ++t)
+      if (cur + t < W) bwd_flush<GH1>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0);
   }
 }
 
@@ -384,6 +400,7 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
   __shared__ __align__(128) float G_s[32 * PER];
   __shared__ TapE xtab[P * kMaxG];
   __shared__ TapE ytab[P * kMaxG];
+  __shared__ YSlots yslots[NW * kMaxG];  // [row pair][sample]
   const int r = blockIdx.x / ngroups;
   const int c0 = (blockIdx.x - r * ngroups) * 32;
   const int nc = min(32, C - c0);
@@ -418,12 +435,17 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
   }
   build_tables<P, NT>(xtab, ytab, g, H, W);
   __syncthreads();
+  for (int t = threadIdx.x; t < NW * g.gh; t += NT) {  // merged row slots of every (row pair, sample)
+    const int j = t / g.gh, i = t - j * g.gh;
+    yslots[j * kMaxG + i] = make_slots(ytab[(2 * j) * g.gh + i], ytab[(2 * j + 1) * g.gh + i], W * C);
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane >= nc) return;
   float* base = img + lane;
   const float* grow = G_s + lane * PER + (2 * warp) * P;
-  if (g.gh == 1) bwd_rows<P, true>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, grow);
-  else bwd_rows<P, false>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, grow);
+  if (g.gh == 1) bwd_rows<P, true>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow);
+  else bwd_rows<P, false>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow);
 }
 
 // ------------------------------------------------------------------------------------------------
