@@ -91,8 +91,37 @@ __device__ __forceinline__ void build_tables(TapE* xtab, TapE* ytab, const RoiGe
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// CPL channels per lane: lane l owns channels l, l+32, ... of the CTA's 32*CPL-channel group (every tap is CPL
+// coalesced 128-byte loads at immediate offsets +128 B, so address arithmetic and control flow are shared).
+template <int CPL>
+struct Vec {
+  float v[CPL];
+};
+
+template <int CPL>
+__device__ __forceinline__ Vec<CPL> vzero() {
+  Vec<CPL> r;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) r.v[k] = 0.f;
+  return r;
+}
+
+template <int CPL>
+__device__ __forceinline__ Vec<CPL> vload(const float* __restrict__ p) {
+  Vec<CPL> r;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) r.v[k] = __ldg(p + 32 * k);
+  return r;
+}
+
+template <int CPL>
+__device__ __forceinline__ void vfma(Vec<CPL>& acc, float w, const Vec<CPL>& x) {
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) acc.v[k] = fmaf(w, x.v[k], acc.v[k]);
+}
+
 // Vertical blend of one footprint column for the warp's two rows: v = sum_i wl_i F[lo_i][x] + wh_i F[hi_i][x].
-// All addressing is "per-lane 64-bit base + 32-bit element offset" so that one IMAD.WIDE forms each address.
+// Addressing is "per-lane 64-bit row pointer + 32-bit element offset of the column".
 template <int GH>
 struct RowTaps {  // GH > 0: row pointers + weights in registers;  GH == 0: read from the table every time
   const float* plo[GH > 0 ? GH : 1];
@@ -114,47 +143,41 @@ __device__ __forceinline__ void load_row_taps(RowTaps<GH>& rt, const float* __re
   }
 }
 
-__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-template <int GH>
+template <int GH, int CPL>
 __device__ __forceinline__ void fwd_column(const float* __restrict__ base, int xo, const RowTaps<GH>& ra,
                                            const RowTaps<GH>& rb, const TapE* ya, const TapE* yb, int gh, int WC,
-                                           float& va, float& vb) {
+                                           Vec<CPL>& va, Vec<CPL>& vb) {
+  va = vzero<CPL>();
+  vb = vzero<CPL>();
   if (GH > 0) {
-    float l[4 * (GH > 0 ? GH : 1)];
+    Vec<CPL> l[4 * (GH > 0 ? GH : 1)];
 #pragma unroll
     for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {  // issue every load of the column before the first use
-      l[4 * i + 0] = __ldg(ra.plo[i] + xo);
-      l[4 * i + 1] = __ldg(ra.phi[i] + xo);
-      l[4 * i + 2] = __ldg(rb.plo[i] + xo);
-      l[4 * i + 3] = __ldg(rb.phi[i] + xo);
+      l[4 * i + 0] = vload<CPL>(ra.plo[i] + xo);
+      l[4 * i + 1] = vload<CPL>(ra.phi[i] + xo);
+      l[4 * i + 2] = vload<CPL>(rb.plo[i] + xo);
+      l[4 * i + 3] = vload<CPL>(rb.phi[i] + xo);
     }
-    float a = 0.f, b = 0.f;
 #pragma unroll
     for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {
-      a = fmaf(ra.wl[i], l[4 * i + 0], a);
-      a = fmaf(ra.wh[i], l[4 * i + 1], a);
-      b = fmaf(rb.wl[i], l[4 * i + 2], b);
-      b = fmaf(rb.wh[i], l[4 * i + 3], b);
+      vfma<CPL>(va, ra.wl[i], l[4 * i + 0]);
+      vfma<CPL>(va, ra.wh[i], l[4 * i + 1]);
+      vfma<CPL>(vb, rb.wl[i], l[4 * i + 2]);
+      vfma<CPL>(vb, rb.wh[i], l[4 * i + 3]);
     }
-    va = a;
-    vb = b;
   } else {
-    float a = 0.f, b = 0.f;
     const float* col = base + xo;
     for (int i = 0; i < gh; ++i) {
       const TapE ea = ya[i], eb = yb[i];
       if (ea.lo >= 0) {
-        a = fmaf(ea.wl, __ldg(col + ea.lo * WC), a);
-        a = fmaf(ea.wh, __ldg(col + ea.hi * WC), a);
+        vfma<CPL>(va, ea.wl, vload<CPL>(col + ea.lo * WC));
+        vfma<CPL>(va, ea.wh, vload<CPL>(col + ea.hi * WC));
       }
       if (eb.lo >= 0) {
-        b = fmaf(eb.wl, __ldg(col + eb.lo * WC), b);
-        b = fmaf(eb.wh, __ldg(col + eb.hi * WC), b);
+        vfma<CPL>(vb, eb.wl, vload<CPL>(col + eb.lo * WC));
+        vfma<CPL>(vb, eb.wh, vload<CPL>(col + eb.hi * WC));
       }
     }
-    va = a;
-    vb = b;
   }
 }
 
@@ -162,37 +185,38 @@ __device__ __forceinline__ void fwd_column(const float* __restrict__ base, int x
 // t-loop runs once when the window just slides, twice when it (re)starts): the first version of this kernel,
 // fully unrolled over the 14 bins, was 21 K SASS instructions and lost 27 % of its issue slots to
 // instruction-cache misses (ncu stall_no_inst).
-#define CDDMSL_FWD_SAMPLE(e, SA, SB)                                              \
-  if ((e).lo >= 0) {                                                              \
-    if ((e).lo != cur) {                                                          \
-      int t = ((e).lo == cur + 1) ? 1 : 0;                                        \
-      if (t) {                                                                    \
-        va0 = va1;                                                                \
-        vb0 = vb1;                                                                \
-      }                                                                           \
-      cur = (e).lo;                                                               \
-      for (; t < 2; ++t) {                                                        \
-        float na = 0.f, nb = 0.f;                                                 \
-        if (cur + t < W) fwd_column<GH>(base, (cur + t) * C, ra, rb, ya, yb, gh, WC, na, nb); \
-        if (t == 0) {                                                             \
-          va0 = na;                                                               \
-          vb0 = nb;                                                               \
-        } else {                                                                  \
-          va1 = na;                                                               \
-          vb1 = nb;                                                               \
-        }                                                                         \
-      }                                                                           \
-    }                                                                             \
-    SA = fmaf((e).wl, va0, SA);                                                   \
-    SA = fmaf((e).wh, va1, SA);                                                   \
-    SB = fmaf((e).wl, vb0, SB);                                                   \
-    SB = fmaf((e).wh, vb1, SB);                                                   \
+#define CDDMSL_FWD_SAMPLE(e, SA, SB)                                                      \
+  if ((e).lo >= 0) {                                                                      \
+    if ((e).lo != cur) {                                                                  \
+      int t = ((e).lo == cur + 1) ? 1 : 0;                                                \
+      if (t) {                                                                            \
+        va0 = va1;                                                                        \
+        vb0 = vb1;                                                                        \
+      }                                                                                   \
+      cur = (e).lo;                                                                       \
+      for (; t < 2; ++t) {                                                                \
+        Vec<CPL> na = vzero<CPL>(), nb = vzero<CPL>();                                    \
+        if (cur + t < W) fwd_column<GH, CPL>(base, (cur + t) * C, ra, rb, ya, yb, gh, WC, na, nb); \
+        if (t == 0) {                                                                     \
+          va0 = na;                                                                       \
+          vb0 = nb;                                                                       \
+        } else {                                                                          \
+          va1 = na;                                                                       \
+          vb1 = nb;                                                                       \
+        }                                                                                 \
+      }                                                                                   \
+    }                                                                                     \
+    vfma<CPL>(SA, (e).wl, va0);                                                           \
+    vfma<CPL>(SA, (e).wh, va1);                                                           \
+    vfma<CPL>(SB, (e).wl, vb0);                                                           \
+    vfma<CPL>(SB, (e).wh, vb1);                                                           \
   }
 
-template <int P, int GH>
-__device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image + channel of this lane */,
+template <int P, int GH, int CPL>
+__device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image + first channel of this lane */,
                                          const TapE* __restrict__ xtab, const TapE* __restrict__ ytab, int gw, int gh,
-                                         int W, int C, int row_a, float* __restrict__ orow) {
+                                         int W, int C, int row_a, float* __restrict__ orow /* tile row of channel lane */,
+                                         int nch /* channels of this lane that exist */) {
   const int WC = W * C;
   RowTaps<GH> ra, rb;
   const TapE* ya = ytab + row_a * gh;
@@ -200,11 +224,11 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
   load_row_taps<GH>(ra, base, ya, WC);
   load_row_taps<GH>(rb, base, yb, WC);
   int cur = -4;
-  float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
+  Vec<CPL> va0 = vzero<CPL>(), va1 = vzero<CPL>(), vb0 = vzero<CPL>(), vb1 = vzero<CPL>();
   const TapE* xt = xtab;
 #pragma unroll 1
   for (int pw = 0; pw < P; pw += 2) {
-    float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
+    Vec<CPL> sa0 = vzero<CPL>(), sb0 = vzero<CPL>(), sa1 = vzero<CPL>(), sb1 = vzero<CPL>();
     for (int ix = 0; ix < gw; ++ix) {
       const TapE e = xt[ix];
       CDDMSL_FWD_SAMPLE(e, sa0, sb0)
@@ -215,9 +239,16 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
       CDDMSL_FWD_SAMPLE(e, sa1, sb1)
     }
     xt += gw;
-    // rows a and b of this lane's channel are 2*P contiguous floats of the output tile
-    *reinterpret_cast<float2*>(orow + pw) = make_float2(sa0, sa1);
-    *reinterpret_cast<float2*>(orow + P + pw) = make_float2(sb0, sb1);
+    // rows a and b of a channel are 2*P contiguous floats of the output tile; channel k of this lane is 32*k
+    // tile rows further on
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      if (k < nch) {
+        float* o = orow + k * 32 * P * P;
+        *reinterpret_cast<float2*>(o + pw) = make_float2(sa0.v[k], sa1.v[k]);
+        *reinterpret_cast<float2*>(o + P + pw) = make_float2(sb0.v[k], sb1.v[k]);
+      }
+    }
   }
 }
 
@@ -241,18 +272,19 @@ __device__ void fwd_direct_any(const float* __restrict__ in, float* __restrict__
   }
 }
 
-template <int P>
-__global__ void __launch_bounds__((P / 2) * 32, 4)
+template <int P, int CPL>
+__global__ void __launch_bounds__((P / 2) * 32, 3)
 roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ in_nchw,
                         const float* __restrict__ rois, float* __restrict__ out, int N, int C, int H, int W, int R,
                         float scale, int sampling_ratio, int aligned, int ngroups) {
-  constexpr int NW = P / 2, NT = NW * 32, PER = P * P;
-  __shared__ __align__(128) float O_s[32 * PER];
-  __shared__ TapE xtab[P * kMaxG];
-  __shared__ TapE ytab[P * kMaxG];
+  constexpr int NW = P / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL;
+  extern __shared__ __align__(128) float dyn_smem[];
+  float* O_s = dyn_smem;                                        // [GC][PER]
+  TapE* xtab = reinterpret_cast<TapE*>(O_s + GC * PER);         // [P * kMaxG]
+  TapE* ytab = xtab + P * kMaxG;
   const int r = blockIdx.x / ngroups;
-  const int c0 = (blockIdx.x - r * ngroups) * 32;
-  const int nc = min(32, C - c0);
+  const int c0 = (blockIdx.x - r * ngroups) * GC;
+  const int nc = min(GC, C - c0);
   const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
   float* out_tile = out + ((size_t)r * C + c0) * PER;
   if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) {
@@ -266,13 +298,20 @@ roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ 
   build_tables<P, NT>(xtab, ytab, g, H, W);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cl = min(lane, nc - 1);  // ragged last group: surplus lanes recompute channel nc-1, never stored
-  const float* base = ft + (size_t)g.batch * H * W * C + c0 + cl;
-  float* orow = O_s + cl * PER + (2 * warp) * P;
-  if (lane < nc) {
-    if (g.gh == 1) fwd_rows<P, 1>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow);
-    else if (g.gh == 2) fwd_rows<P, 2>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow);
-    else fwd_rows<P, 0>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow);
+  // channels of this lane: c0 + lane + 32k.  A ragged last group clamps the LOAD channel (so surplus lanes read
+  // valid memory) and masks the store.
+  const int nch = lane < nc ? min(CPL, (nc - lane + 31) / 32) : 0;
+  if (nch > 0) {
+    // loads of channel k >= nch would run past C: fold them onto channel 0 of the lane by using CPL' = nch
+    const float* base = ft + (size_t)g.batch * H * W * C + c0 + lane;
+    float* orow = O_s + lane * PER + (2 * warp) * P;
+    if (nch == CPL) {
+      if (g.gh == 1) fwd_rows<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
+      else if (g.gh == 2) fwd_rows<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
+      else fwd_rows<P, 0, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
+    } else {
+      fwd_rows<P, 0, 1>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 1);  // ragged tail: one channel
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -324,86 +363,106 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 }
 
 // dF[y][x][c] += Ay^T (ta, tb) for one footprint column
-template <bool GH1>
+template <bool GH1, int CPL>
 __device__ __forceinline__ void bwd_flush(float* __restrict__ base, int xo, const YSlots& s1,
-                                          const YSlots* __restrict__ slots, int gh, float ta, float tb) {
+                                          const YSlots* __restrict__ slots, int gh, const Vec<CPL>& ta,
+                                          const Vec<CPL>& tb, int nch) {
   if (GH1) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (s1.off[k] >= 0) red_add(base + (s1.off[k] + xo), fmaf(s1.wa[k], ta, s1.wb[k] * tb));
+      if (s1.off[k] >= 0) {
+        float* p = base + (s1.off[k] + xo);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+          if (q < nch) red_add(p + 32 * q, fmaf(s1.wa[k], ta.v[q], s1.wb[k] * tb.v[q]));
+      }
   } else {
     for (int i = 0; i < gh; ++i) {
       const YSlots s = slots[i];  // 3 x LDS.128, warp-uniform
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (s.off[k] >= 0) red_add(base + (s.off[k] + xo), fmaf(s.wa[k], ta, s.wb[k] * tb));
+        if (s.off[k] >= 0) {
+          float* p = base + (s.off[k] + xo);
+#pragma unroll
+          for (int q = 0; q < CPL; ++q)
+            if (q < nch) red_add(p + 32 * q, fmaf(s.wa[k], ta.v[q], s.wb[k] * tb.v[q]));
+        }
     }
   }
 }
 
-#define CDDMSL_BWD_SAMPLE(e, GA, GB)                                                        \
-  if ((e).lo >= 0) {                                                                        \
-    if ((e).lo != cur) {                                                                    \
-      if (cur >= 0) {                                                                       \
-        const bool adj = ((e).lo == cur + 1);                                               \
-        const int nfl = adj ? 1 : 2;                                                        \
-        for (int t = 0; t < nfl; ++t)                                                       \
-          if (cur + t < W)                                                                  \
-            bwd_flush<GH1>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0); \
-        ta0 = adj ? ta1 : 0.f;                                                              \
-        tb0 = adj ? tb1 : 0.f;                                                              \
-      }                                                                                     \
-      ta1 = tb1 = 0.f;                                                                      \
-      cur = (e).lo;                                                                         \
-    }                                                                                       \
-    ta0 = fmaf((e).wl, GA, ta0);                                                            \
-    ta1 = fmaf((e).wh, GA, ta1);                                                            \
-    tb0 = fmaf((e).wl, GB, tb0);                                                            \
-    tb1 = fmaf((e).wh, GB, tb1);                                                            \
+#define CDDMSL_BWD_SAMPLE(e, COMP)                                                                 \
+  if ((e).lo >= 0) {                                                                               \
+    if ((e).lo != cur) {                                                                           \
+      if (cur >= 0) {                                                                              \
+        const bool adj = ((e).lo == cur + 1);                                                      \
+        const int nfl = adj ? 1 : 2;                                                               \
+        for (int t = 0; t < nfl; ++t)                                                              \
+          if (cur + t < W)                                                                         \
+            bwd_flush<GH1, CPL>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0, nch); \
+        ta0 = adj ? ta1 : vzero<CPL>();                                                            \
+        tb0 = adj ? tb1 : vzero<CPL>();                                                            \
+      }                                                                                            \
+      ta1 = vzero<CPL>();                                                                          \
+      tb1 = vzero<CPL>();                                                                          \
+      cur = (e).lo;                                                                                \
+    }                                                                                              \
+    _Pragma("unroll") for (int q = 0; q < CPL; ++q) {                                              \
+      ta0.v[q] = fmaf((e).wl, ga[q].COMP, ta0.v[q]);                                               \
+      ta1.v[q] = fmaf((e).wh, ga[q].COMP, ta1.v[q]);                                               \
+      tb0.v[q] = fmaf((e).wl, gb[q].COMP, tb0.v[q]);                                               \
+      tb1.v[q] = fmaf((e).wh, gb[q].COMP, tb1.v[q]);                                               \
+    }                                                                                              \
   }
 
-template <int P, bool GH1>
+template <int P, bool GH1, int CPL>
 __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* __restrict__ xtab,
                                          const YSlots* __restrict__ slots, int gw, int gh, int W, int C,
-                                         const float* __restrict__ grow) {
+                                         const float* __restrict__ grow, int nch) {
   YSlots s1;
   if (GH1) s1 = slots[0];
   int cur = -4;
-  float ta0 = 0.f, ta1 = 0.f, tb0 = 0.f, tb1 = 0.f;
+  Vec<CPL> ta0 = vzero<CPL>(), ta1 = vzero<CPL>(), tb0 = vzero<CPL>(), tb1 = vzero<CPL>();
   const TapE* xt = xtab;
 #pragma unroll 1
   for (int pw = 0; pw < P; pw += 2) {
-    const float2 ga = *reinterpret_cast<const float2*>(grow + pw);
-    const float2 gb = *reinterpret_cast<const float2*>(grow + P + pw);
+    float2 ga[CPL], gb[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const float* gq = grow + (q < nch ? q : 0) * 32 * P * P;
+      ga[q] = *reinterpret_cast<const float2*>(gq + pw);
+      gb[q] = *reinterpret_cast<const float2*>(gq + P + pw);
+    }
     for (int ix = 0; ix < gw; ++ix) {
       const TapE e = xt[ix];
-      CDDMSL_BWD_SAMPLE(e, ga.x, gb.x)
+      CDDMSL_BWD_SAMPLE(e, x)
     }
     xt += gw;
     for (int ix = 0; ix < gw; ++ix) {
       const TapE e = xt[ix];
-      CDDMSL_BWD_SAMPLE(e, ga.y, gb.y)
+      CDDMSL_BWD_SAMPLE(e, y)
     }
     xt += gw;
   }
   if (cur >= 0) {
     for (int t = 0; t < 2; ++t)
-      if (cur + t < W) bwd_flush<GH1>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0);
+      if (cur + t < W) bwd_flush<GH1, CPL>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0, nch);
   }
 }
 
-template <int P>
-__global__ void __launch_bounds__((P / 2) * 32, 4)
+template <int P, int CPL>
+__global__ void __launch_bounds__((P / 2) * 32, 3)
 roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict__ rois, float* __restrict__ gt, int N,
                         int C, int H, int W, int R, float scale, int sampling_ratio, int aligned, int ngroups) {
-  constexpr int NW = P / 2, NT = NW * 32, PER = P * P;
-  __shared__ __align__(128) float G_s[32 * PER];
-  __shared__ TapE xtab[P * kMaxG];
-  __shared__ TapE ytab[P * kMaxG];
-  __shared__ YSlots yslots[NW * kMaxG];  // [row pair][sample]
+  constexpr int NW = P / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL;
+  extern __shared__ __align__(128) float dyn_smem[];
+  float* G_s = dyn_smem;                                   // [GC][PER]
+  TapE* xtab = reinterpret_cast<TapE*>(G_s + GC * PER);    // [P * kMaxG]
+  TapE* ytab = xtab + P * kMaxG;
+  YSlots* yslots = reinterpret_cast<YSlots*>(ytab + P * kMaxG);  // [NW][kMaxG]: [row pair][sample]
   const int r = blockIdx.x / ngroups;
-  const int c0 = (blockIdx.x - r * ngroups) * 32;
-  const int nc = min(32, C - c0);
+  const int c0 = (blockIdx.x - r * ngroups) * GC;
+  const int nc = min(GC, C - c0);
   const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
   if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) return;
   const float* g_tile = gout + ((size_t)r * C + c0) * PER;
@@ -441,11 +500,12 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane >= nc) return;
+  const int nch = lane < nc ? min(CPL, (nc - lane + 31) / 32) : 0;
+  if (nch == 0) return;
   float* base = img + lane;
   const float* grow = G_s + lane * PER + (2 * warp) * P;
-  if (g.gh == 1) bwd_rows<P, true>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow);
-  else bwd_rows<P, false>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow);
+  if (g.gh == 1) bwd_rows<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
+  else bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -458,29 +518,54 @@ bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW) {
 
 size_t roi_cl_workspace_bytes(int N, int C, int H, int W) { return align_up((size_t)N * C * H * W * 4, 256); }
 
+int g_fwd_cpl = 2, g_bwd_cpl = 2;  // channels per lane (tuning knobs "roi_fwd_cpl" / "roi_bwd_cpl")
+
+template <int CPL>
+static int launch_fwd_cl(const float* ft, const float* in, const float* rois, float* out, int N, int C, int H, int W,
+                         int R, float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
+  const int ngroups = ceil_div(C, 32 * CPL);
+  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
+  const int smem = 32 * CPL * 196 * 4 + 2 * 14 * kMaxG * (int)sizeof(TapE);
+  auto k = roi_align_fwd_cl_kernel<14, CPL>;
+  cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ea != cudaSuccess) return (int)ea;
+  k<<<(unsigned)((long long)R * ngroups), 7 * 32, smem, stream>>>(ft, in, rois, out, N, C, H, W, R, scale,
+                                                                  sampling_ratio, aligned, ngroups);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <int CPL>
+static int launch_bwd_cl(const float* gout, const float* rois, float* gt, int N, int C, int H, int W, int R,
+                         float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
+  const int ngroups = ceil_div(C, 32 * CPL);
+  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
+  const int smem = 32 * CPL * 196 * 4 + 2 * 14 * kMaxG * (int)sizeof(TapE) + 7 * kMaxG * (int)sizeof(YSlots);
+  auto k = roi_align_bwd_cl_kernel<14, CPL>;
+  cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ea != cudaSuccess) return (int)ea;
+  k<<<(unsigned)((long long)R * ngroups), 7 * 32, smem, stream>>>(gout, rois, gt, N, C, H, W, R, scale,
+                                                                  sampling_ratio, aligned, ngroups);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, float scale,
                      int sampling_ratio, int aligned, float* ft, cudaStream_t stream) {
   int rc = launch_transpose(in, ft, N, C, H * W, stream);  // NCHW -> NHWC
   if (rc) return rc;
-  const int ngroups = ceil_div(C, 32);
-  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
-  roi_align_fwd_cl_kernel<14><<<(unsigned)((long long)R * ngroups), 7 * 32, 0, stream>>>(
-      ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, ngroups);
-  count_launch();
-  return (int)cudaGetLastError();
+  return g_fwd_cpl == 2 ? launch_fwd_cl<2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+                        : launch_fwd_cl<1>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
 }
 
 int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, float scale,
                      int sampling_ratio, int aligned, float* gt, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(gt, 0, (size_t)N * C * H * W * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
-  const int ngroups = ceil_div(C, 32);
-  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
-  roi_align_bwd_cl_kernel<14><<<(unsigned)((long long)R * ngroups), 7 * 32, 0, stream>>>(
-      gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, ngroups);
-  count_launch();
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
+  int rc = g_bwd_cpl == 2
+               ? launch_bwd_cl<2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+               : launch_bwd_cl<1>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
+  if (rc) return rc;
   return launch_transpose(gt, gin, N, H * W, C, stream);  // NHWC -> NCHW (overwrites gin completely)
 }
 
