@@ -333,8 +333,15 @@ def run_ours(args):
     dom = "roi_align_bwd" if seg[3] >= seg[0] else "roi_align_fwd"
     ach = kern[dom]["gbs"]
     step_bytes = 2 * bytes_roi + head_bytes
+    traffic = None
+    try:  # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["kernels"]
+        key = "roi_align_bwd_cl_kernel" if dom == "roi_align_bwd" else "roi_align_fwd_cl_kernel"
+        traffic = next(v["dram_bytes"] for k, v in tj.items() if k.startswith(key)) if args.workload == "voc" else None
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "step_frac": (step_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
                 "step_algorithmic_bytes": step_bytes}
 
