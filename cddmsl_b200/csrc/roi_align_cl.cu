@@ -22,7 +22,8 @@
 
 namespace cddmsl {
 
-constexpr int kMaxG = 16;  // samples per bin and axis that fit the tap tables (RoIs up to 224 cells)
+constexpr int kMaxG = 10;  // samples per bin and axis that fit the tap tables (RoIs up to 140 cells); sized so that
+                            // 4 CTAs of the 2-channel-per-lane kernels share one SM's 227 KB of shared memory
 
 struct __align__(16) TapE {
   int lo;    // absolute column / row index of the low tap, -1: sample contributes nothing
@@ -64,27 +65,27 @@ int launch_transpose(const float* in, float* out, int N, int A, int B, cudaStrea
 // ------------------------------------------------------------------------------------------------
 // shared prologue: per-RoI tap tables
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ TapE make_tap_entry(float start, float bin, int p, int i, int g, int L, float wscale) {
+  const Tap tp = make_tap(start, bin, p, i, g, L, 0);
+  TapE e;
+  e.lo = (tp.wl == 0.f && tp.wh == 0.f) ? -1 : tp.lo;
+  e.hi = tp.hi;
+  e.wl = tp.wl * wscale;
+  e.wh = tp.wh * wscale;
+  return e;
+}
+
 template <int P, int NT>
 __device__ __forceinline__ void build_tables(TapE* xtab, TapE* ytab, const RoiGeom& g, int H, int W) {
   for (int t = threadIdx.x; t < P * g.gw; t += NT) {
     const int p = t / g.gw, i = t - p * g.gw;
-    const Tap tp = make_tap(g.sw, g.bw, p, i, g.gw, W, 0);
-    TapE e;
-    e.lo = (tp.wl == 0.f && tp.wh == 0.f) ? -1 : tp.lo;
-    e.hi = tp.hi;
-    e.wl = tp.wl * g.inv_count;
-    e.wh = tp.wh * g.inv_count;
-    xtab[t] = e;
+    xtab[t] = make_tap_entry(g.sw, g.bw, p, i, g.gw, W, g.inv_count);
   }
-  for (int t = threadIdx.x; t < P * g.gh; t += NT) {
-    const int p = t / g.gh, i = t - p * g.gh;
-    const Tap tp = make_tap(g.sh, g.bh, p, i, g.gh, H, 0);
-    TapE e;
-    e.lo = (tp.wl == 0.f && tp.wh == 0.f) ? -1 : tp.lo;
-    e.hi = tp.hi;
-    e.wl = tp.wl;
-    e.wh = tp.wh;
-    ytab[t] = e;
+  if (ytab) {
+    for (int t = threadIdx.x; t < P * g.gh; t += NT) {
+      const int p = t / g.gh, i = t - p * g.gh;
+      ytab[t] = make_tap_entry(g.sh, g.bh, p, i, g.gh, H, 1.f);
+    }
   }
 }
 
@@ -273,7 +274,7 @@ __device__ void fwd_direct_any(const float* __restrict__ in, float* __restrict__
 }
 
 template <int P, int CPL>
-__global__ void __launch_bounds__((P / 2) * 32, 3)
+__global__ void __launch_bounds__((P / 2) * 32, 4)
 roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ in_nchw,
                         const float* __restrict__ rois, float* __restrict__ out, int N, int C, int H, int W, int R,
                         float scale, int sampling_ratio, int aligned, int ngroups) {
@@ -451,15 +452,14 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
 }
 
 template <int P, int CPL>
-__global__ void __launch_bounds__((P / 2) * 32, 3)
+__global__ void __launch_bounds__((P / 2) * 32, 4)
 roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict__ rois, float* __restrict__ gt, int N,
                         int C, int H, int W, int R, float scale, int sampling_ratio, int aligned, int ngroups) {
   constexpr int NW = P / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL;
   extern __shared__ __align__(128) float dyn_smem[];
   float* G_s = dyn_smem;                                   // [GC][PER]
   TapE* xtab = reinterpret_cast<TapE*>(G_s + GC * PER);    // [P * kMaxG]
-  TapE* ytab = xtab + P * kMaxG;
-  YSlots* yslots = reinterpret_cast<YSlots*>(ytab + P * kMaxG);  // [NW][kMaxG]: [row pair][sample]
+  YSlots* yslots = reinterpret_cast<YSlots*>(xtab + P * kMaxG);  // [NW][kMaxG]: [row pair][sample]
   const int r = blockIdx.x / ngroups;
   const int c0 = (blockIdx.x - r * ngroups) * GC;
   const int nc = min(GC, C - c0);
@@ -492,11 +492,11 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
     float4* d4 = reinterpret_cast<float4*>(G_s);
     for (int e = threadIdx.x; e < nc * PER / 4; e += NT) d4[e] = __ldcs(s4 + e);
   }
-  build_tables<P, NT>(xtab, ytab, g, H, W);
-  __syncthreads();
+  build_tables<P, NT>(xtab, nullptr, g, H, W);
   for (int t = threadIdx.x; t < NW * g.gh; t += NT) {  // merged row slots of every (row pair, sample)
     const int j = t / g.gh, i = t - j * g.gh;
-    yslots[j * kMaxG + i] = make_slots(ytab[(2 * j) * g.gh + i], ytab[(2 * j + 1) * g.gh + i], W * C);
+    yslots[j * kMaxG + i] = make_slots(make_tap_entry(g.sh, g.bh, 2 * j, i, g.gh, H, 1.f),
+                                       make_tap_entry(g.sh, g.bh, 2 * j + 1, i, g.gh, H, 1.f), W * C);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -540,7 +540,7 @@ static int launch_bwd_cl(const float* gout, const float* rois, float* gt, int N,
                          float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
   const int ngroups = ceil_div(C, 32 * CPL);
   if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
-  const int smem = 32 * CPL * 196 * 4 + 2 * 14 * kMaxG * (int)sizeof(TapE) + 7 * kMaxG * (int)sizeof(YSlots);
+  const int smem = 32 * CPL * 196 * 4 + 14 * kMaxG * (int)sizeof(TapE) + 7 * kMaxG * (int)sizeof(YSlots);
   auto k = roi_align_bwd_cl_kernel<14, CPL>;
   cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ea != cudaSuccess) return (int)ea;
