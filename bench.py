@@ -269,12 +269,30 @@ def run_ours(args):
         h2d = sum(t.numel() * t.element_size() for t in [h_feat, h_rois, hx, hgt] + h_align)
         d2h = sum(t.numel() * t.element_size() for t in [o_gin, o_dx, o_sc] + o_ga)
 
-        def e2e_step():
-            f = h_feat.to(dev, non_blocking=True).requires_grad_(True)
-            r = h_rois.to(dev, non_blocking=True)
-            xx = hx.to(dev, non_blocking=True).requires_grad_(True)
-            gg = hgt.to(dev, non_blocking=True)
-            al = [t.to(dev, non_blocking=True).requires_grad_(True) for t in h_align]
+        # Three streams, double-buffered device inputs: H2D of step i+1 and D2H of step i-1 overlap the compute of
+        # step i (what a real input pipeline does).  Every byte still crosses PCIe inside the timed region.
+        s_h2d, s_d2h, s_cmp = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+        host_in = [h_feat, h_rois, hx, hgt] + h_align
+        dev_in = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+
+        def issue_h2d(i):
+            b = i & 1
+            with torch.cuda.stream(s_h2d):
+                s_h2d.wait_event(ev_cmp[b])          # the compute that last read this buffer set is done
+                for d, h in zip(dev_in[b], host_in):
+                    d.copy_(h, non_blocking=True)
+                ev_in[b].record(s_h2d)
+
+        def e2e_step(i):
+            b = i & 1
+            s_cmp.wait_event(ev_in[b])
+            f = dev_in[b][0].detach().requires_grad_(True)
+            r, gg = dev_in[b][1], dev_in[b][3]
+            xx = dev_in[b][2].detach().requires_grad_(True)
+            al = [t.detach().requires_grad_(True) for t in dev_in[b][4:]]
             out = pooler(f, r)
             inst = Instances((cfg.img_h, cfg.img_w))
             inst.proposal_boxes = Boxes(r[:, 1:] + r.new_tensor([0.0, 0.0, 1.0, 1.0]))  # box-reg branch wants w,h > 0
@@ -284,20 +302,32 @@ def run_ours(args):
             li = image_caption_consistency_loss(al[1], al[0])
             lr = caption_consistency_loss(al[2], al[3])
             torch.autograd.backward([out, lc, li, lr], [out.detach(), one[0], one[0], one[0]])
-            o_gin.copy_(f.grad, non_blocking=True)
-            o_dx.copy_(xx.grad, non_blocking=True)
-            for o, t in zip(o_ga, al):
-                o.copy_(t.grad, non_blocking=True)
-            o_sc.copy_(torch.stack([lc.detach(), li.detach(), lr.detach(), lc.detach() * 0]), non_blocking=True)
+            sc = torch.stack([lc.detach(), li.detach(), lr.detach(), lc.detach() * 0])
+            ev_cmp[b].record(s_cmp)
+            grads = [f.grad, xx.grad, sc] + [t.grad for t in al]
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_cmp[b])
+                for o, gsrc in zip([o_gin, o_dx, o_sc] + o_ga, grads):
+                    gsrc.record_stream(s_d2h)
+                    o.copy_(gsrc, non_blocking=True)
+                ev_out[b].record(s_d2h)
 
-        for _ in range(3):
-            e2e_step()
+        def run_e2e(n):
+            issue_h2d(0)
+            for i in range(n):
+                if i + 1 < n:
+                    issue_h2d(i + 1)
+                e2e_step(i)
+            s_cmp.wait_event(ev_out[(n - 1) & 1])
+            if n > 1:
+                s_cmp.wait_event(ev_out[(n - 2) & 1])
+
+        run_e2e(3)
         barrier()
-        k2 = max(3, args.steps // 2)
+        k2 = max(4, args.steps // 2)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(k2):
-            e2e_step()
+        run_e2e(k2)
         s1.record()
         barrier()
         ms2 = s0.elapsed_time(s1)
@@ -307,7 +337,8 @@ def run_ours(args):
             ms2 = float(tt.item())
         e2e = {"value": world * R * k2 / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms2 / k2, "steps": k2,
-               "api": "ROIAlign.forward + FastRCNNOutputLayers.forward/losses + caption_consistency_loss + autograd"}
+               "api": "ROIAlign.forward + FastRCNNOutputLayers.forward/losses + caption_consistency_loss + autograd",
+               "pipelining": "H2D(i+1) and D2H(i-1) on side streams overlap compute(i); all copies inside the timed region"}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
