@@ -115,6 +115,18 @@ __device__ __forceinline__ Vec<CPL> vload(const float* __restrict__ p) {
   return r;
 }
 
+// row pointer (64-bit, per lane) + column byte offset (32-bit, warp-uniform): two integer instructions per
+// address instead of the four (IADD3/IMAD.X/LEA/LEA.HI.X) the compiler emits for `ptr + idx`.
+template <int CPL>
+__device__ __forceinline__ Vec<CPL> vload_off(const float* __restrict__ rowp, unsigned xb) {
+  Vec<CPL> r;
+  unsigned long long a;
+  asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tadd.u64 %0, %2, t;\n\t}" : "=l"(a) : "r"(xb), "l"(rowp));
+  asm("ld.global.nc.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(a));
+  if (CPL > 1) asm("ld.global.nc.f32 %0, [%1+128];" : "=f"(r.v[CPL > 1 ? 1 : 0]) : "l"(a));
+  return r;
+}
+
 template <int CPL>
 __device__ __forceinline__ void vfma(Vec<CPL>& acc, float w, const Vec<CPL>& x) {
 #pragma unroll
@@ -145,7 +157,7 @@ __device__ __forceinline__ void load_row_taps(RowTaps<GH>& rt, const float* __re
 }
 
 template <int GH, int CPL>
-__device__ __forceinline__ void fwd_column(const float* __restrict__ base, int xo, const RowTaps<GH>& ra,
+__device__ __forceinline__ void fwd_column(const float* __restrict__ base, unsigned xo, const RowTaps<GH>& ra,
                                            const RowTaps<GH>& rb, const TapE* ya, const TapE* yb, int gh, int WC,
                                            Vec<CPL>& va, Vec<CPL>& vb) {
   va = vzero<CPL>();
@@ -154,10 +166,10 @@ __device__ __forceinline__ void fwd_column(const float* __restrict__ base, int x
     Vec<CPL> l[4 * (GH > 0 ? GH : 1)];
 #pragma unroll
     for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {  // issue every load of the column before the first use
-      l[4 * i + 0] = vload<CPL>(ra.plo[i] + xo);
-      l[4 * i + 1] = vload<CPL>(ra.phi[i] + xo);
-      l[4 * i + 2] = vload<CPL>(rb.plo[i] + xo);
-      l[4 * i + 3] = vload<CPL>(rb.phi[i] + xo);
+      l[4 * i + 0] = vload_off<CPL>(ra.plo[i], xo);
+      l[4 * i + 1] = vload_off<CPL>(ra.phi[i], xo);
+      l[4 * i + 2] = vload_off<CPL>(rb.plo[i], xo);
+      l[4 * i + 3] = vload_off<CPL>(rb.phi[i], xo);
     }
 #pragma unroll
     for (int i = 0; i < (GH > 0 ? GH : 0); ++i) {
@@ -167,16 +179,15 @@ __device__ __forceinline__ void fwd_column(const float* __restrict__ base, int x
       vfma<CPL>(vb, rb.wh[i], l[4 * i + 3]);
     }
   } else {
-    const float* col = base + xo;
     for (int i = 0; i < gh; ++i) {
       const TapE ea = ya[i], eb = yb[i];
       if (ea.lo >= 0) {
-        vfma<CPL>(va, ea.wl, vload<CPL>(col + ea.lo * WC));
-        vfma<CPL>(va, ea.wh, vload<CPL>(col + ea.hi * WC));
+        vfma<CPL>(va, ea.wl, vload_off<CPL>(base, xo + (unsigned)(ea.lo * WC) * 4u));
+        vfma<CPL>(va, ea.wh, vload_off<CPL>(base, xo + (unsigned)(ea.hi * WC) * 4u));
       }
       if (eb.lo >= 0) {
-        vfma<CPL>(vb, eb.wl, vload<CPL>(col + eb.lo * WC));
-        vfma<CPL>(vb, eb.wh, vload<CPL>(col + eb.hi * WC));
+        vfma<CPL>(vb, eb.wl, vload_off<CPL>(base, xo + (unsigned)(eb.lo * WC) * 4u));
+        vfma<CPL>(vb, eb.wh, vload_off<CPL>(base, xo + (unsigned)(eb.hi * WC) * 4u));
       }
     }
   }
@@ -186,31 +197,23 @@ __device__ __forceinline__ void fwd_column(const float* __restrict__ base, int x
 // t-loop runs once when the window just slides, twice when it (re)starts): the first version of this kernel,
 // fully unrolled over the 14 bins, was 21 K SASS instructions and lost 27 % of its issue slots to
 // instruction-cache misses (ncu stall_no_inst).
-#define CDDMSL_FWD_SAMPLE(e, SA, SB)                                                      \
-  if ((e).lo >= 0) {                                                                      \
-    if ((e).lo != cur) {                                                                  \
-      int t = ((e).lo == cur + 1) ? 1 : 0;                                                \
-      if (t) {                                                                            \
-        va0 = va1;                                                                        \
-        vb0 = vb1;                                                                        \
-      }                                                                                   \
-      cur = (e).lo;                                                                       \
-      for (; t < 2; ++t) {                                                                \
-        Vec<CPL> na = vzero<CPL>(), nb = vzero<CPL>();                                    \
-        if (cur + t < W) fwd_column<GH, CPL>(base, (cur + t) * C, ra, rb, ya, yb, gh, WC, na, nb); \
-        if (t == 0) {                                                                     \
-          va0 = na;                                                                       \
-          vb0 = nb;                                                                       \
-        } else {                                                                          \
-          va1 = na;                                                                       \
-          vb1 = nb;                                                                       \
-        }                                                                                 \
-      }                                                                                   \
-    }                                                                                     \
-    vfma<CPL>(SA, (e).wl, va0);                                                           \
-    vfma<CPL>(SA, (e).wh, va1);                                                           \
-    vfma<CPL>(SB, (e).wl, vb0);                                                           \
-    vfma<CPL>(SB, (e).wh, vb1);                                                           \
+#define CDDMSL_FWD_SAMPLE(e, SA, SB)                                                        \
+  if ((e).lo >= 0) {                                                                        \
+    if ((e).lo != cur) {                                                                    \
+      if ((e).lo == cur + 1) {                                                              \
+        va0 = va1;                                                                          \
+        vb0 = vb1;                                                                          \
+      } else {                                                                              \
+        fwd_column<GH, CPL>(base, (unsigned)(e).lo * Cb, ra, rb, ya, yb, gh, WC, va0, vb0); \
+      }                                                                                     \
+      cur = (e).lo;                                                                         \
+      /* hi == min(lo+1, W-1): always a valid column (weight 0 when clamped) */             \
+      fwd_column<GH, CPL>(base, (unsigned)(e).hi * Cb, ra, rb, ya, yb, gh, WC, va1, vb1);   \
+    }                                                                                       \
+    vfma<CPL>(SA, (e).wl, va0);                                                             \
+    vfma<CPL>(SA, (e).wh, va1);                                                             \
+    vfma<CPL>(SB, (e).wl, vb0);                                                             \
+    vfma<CPL>(SB, (e).wh, vb1);                                                             \
   }
 
 template <int P, int GH, int CPL>
@@ -219,6 +222,7 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
                                          int W, int C, int row_a, float* __restrict__ orow /* tile row of channel lane */,
                                          int nch /* channels of this lane that exist */) {
   const int WC = W * C;
+  const unsigned Cb = (unsigned)C * 4u;  // bytes between two columns of the channels-last map
   RowTaps<GH> ra, rb;
   const TapE* ya = ytab + row_a * gh;
   const TapE* yb = ya + gh;
@@ -363,19 +367,28 @@ __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// dF[y][x][c] += Ay^T (ta, tb) for one footprint column
+// lane base pointer (64-bit) + byte offset (32-bit): CPL coalesced 128-byte reductions 128 B apart
+template <int CPL>
+__device__ __forceinline__ void red_add_off(float* base, unsigned ob, const float* v, int nch) {
+  unsigned long long a;
+  asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tadd.u64 %0, %2, t;\n\t}" : "=l"(a) : "r"(ob), "l"(base));
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(a), "f"(v[0]) : "memory");
+  if (CPL > 1 && nch > 1) asm volatile("red.global.add.f32 [%0+128], %1;" ::"l"(a), "f"(v[CPL > 1 ? 1 : 0]) : "memory");
+}
+
+// dF[y][x][c] += Ay^T (ta, tb) for one footprint column (xb = column byte offset; slot offsets are in elements)
 template <bool GH1, int CPL>
-__device__ __forceinline__ void bwd_flush(float* __restrict__ base, int xo, const YSlots& s1,
+__device__ __forceinline__ void bwd_flush(float* __restrict__ base, unsigned xb, const YSlots& s1,
                                           const YSlots* __restrict__ slots, int gh, const Vec<CPL>& ta,
                                           const Vec<CPL>& tb, int nch) {
   if (GH1) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (s1.off[k] >= 0) {
-        float* p = base + (s1.off[k] + xo);
+        float v[CPL];
 #pragma unroll
-        for (int q = 0; q < CPL; ++q)
-          if (q < nch) red_add(p + 32 * q, fmaf(s1.wa[k], ta.v[q], s1.wb[k] * tb.v[q]));
+        for (int q = 0; q < CPL; ++q) v[q] = fmaf(s1.wa[k], ta.v[q], s1.wb[k] * tb.v[q]);
+        red_add_off<CPL>(base, xb + (unsigned)s1.off[k] * 4u, v, nch);
       }
   } else {
     for (int i = 0; i < gh; ++i) {
@@ -383,37 +396,40 @@ __device__ __forceinline__ void bwd_flush(float* __restrict__ base, int xo, cons
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (s.off[k] >= 0) {
-          float* p = base + (s.off[k] + xo);
+          float v[CPL];
 #pragma unroll
-          for (int q = 0; q < CPL; ++q)
-            if (q < nch) red_add(p + 32 * q, fmaf(s.wa[k], ta.v[q], s.wb[k] * tb.v[q]));
+          for (int q = 0; q < CPL; ++q) v[q] = fmaf(s.wa[k], ta.v[q], s.wb[k] * tb.v[q]);
+          red_add_off<CPL>(base, xb + (unsigned)s.off[k] * 4u, v, nch);
         }
     }
   }
 }
 
-#define CDDMSL_BWD_SAMPLE(e, COMP)                                                                 \
-  if ((e).lo >= 0) {                                                                               \
-    if ((e).lo != cur) {                                                                           \
-      if (cur >= 0) {                                                                              \
-        const bool adj = ((e).lo == cur + 1);                                                      \
-        const int nfl = adj ? 1 : 2;                                                               \
-        for (int t = 0; t < nfl; ++t)                                                              \
-          if (cur + t < W)                                                                         \
-            bwd_flush<GH1, CPL>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0, nch); \
-        ta0 = adj ? ta1 : vzero<CPL>();                                                            \
-        tb0 = adj ? tb1 : vzero<CPL>();                                                            \
-      }                                                                                            \
-      ta1 = vzero<CPL>();                                                                          \
-      tb1 = vzero<CPL>();                                                                          \
-      cur = (e).lo;                                                                                \
-    }                                                                                              \
-    _Pragma("unroll") for (int q = 0; q < CPL; ++q) {                                              \
-      ta0.v[q] = fmaf((e).wl, ga[q].COMP, ta0.v[q]);                                               \
-      ta1.v[q] = fmaf((e).wh, ga[q].COMP, ta1.v[q]);                                               \
-      tb0.v[q] = fmaf((e).wl, gb[q].COMP, tb0.v[q]);                                               \
-      tb1.v[q] = fmaf((e).wh, gb[q].COMP, tb1.v[q]);                                               \
-    }                                                                                              \
+#define CDDMSL_BWD_SAMPLE(e, COMP)                                                            \
+  if ((e).lo >= 0) {                                                                          \
+    if ((e).lo != cur) {                                                                      \
+      if (cur >= 0) {                                                                         \
+        bwd_flush<GH1, CPL>(base, (unsigned)cur * Cb, s1, slots, gh, ta0, tb0, nch);          \
+        if ((e).lo == cur + 1) {                                                              \
+          ta0 = ta1;                                                                          \
+          tb0 = tb1;                                                                          \
+        } else {                                                                              \
+          if (curhi != cur) bwd_flush<GH1, CPL>(base, (unsigned)curhi * Cb, s1, slots, gh, ta1, tb1, nch); \
+          ta0 = vzero<CPL>();                                                                 \
+          tb0 = vzero<CPL>();                                                                 \
+        }                                                                                     \
+      }                                                                                       \
+      ta1 = vzero<CPL>();                                                                     \
+      tb1 = vzero<CPL>();                                                                     \
+      cur = (e).lo;                                                                           \
+      curhi = (e).hi;                                                                         \
+    }                                                                                         \
+    _Pragma("unroll") for (int q = 0; q < CPL; ++q) {                                         \
+      ta0.v[q] = fmaf((e).wl, ga[q].COMP, ta0.v[q]);                                          \
+      ta1.v[q] = fmaf((e).wh, ga[q].COMP, ta1.v[q]);                                          \
+      tb0.v[q] = fmaf((e).wl, gb[q].COMP, tb0.v[q]);                                          \
+      tb1.v[q] = fmaf((e).wh, gb[q].COMP, tb1.v[q]);                                          \
+    }                                                                                         \
   }
 
 template <int P, bool GH1, int CPL>
@@ -422,7 +438,8 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
                                          const float* __restrict__ grow, int nch) {
   YSlots s1;
   if (GH1) s1 = slots[0];
-  int cur = -4;
+  const unsigned Cb = (unsigned)C * 4u;
+  int cur = -4, curhi = -4;
   Vec<CPL> ta0 = vzero<CPL>(), ta1 = vzero<CPL>(), tb0 = vzero<CPL>(), tb1 = vzero<CPL>();
   const TapE* xt = xtab;
 #pragma unroll 1
@@ -446,8 +463,8 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
     xt += gw;
   }
   if (cur >= 0) {
-    for (int t = 0; t < 2; ++t)
-      if (cur + t < W) bwd_flush<GH1, CPL>(base, (cur + t) * C, s1, slots, gh, t ? ta1 : ta0, t ? tb1 : tb0, nch);
+    bwd_flush<GH1, CPL>(base, (unsigned)cur * Cb, s1, slots, gh, ta0, tb0, nch);
+    if (curhi != cur) bwd_flush<GH1, CPL>(base, (unsigned)curhi * Cb, s1, slots, gh, ta1, tb1, nch);
   }
 }
 
