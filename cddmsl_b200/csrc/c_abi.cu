@@ -7,6 +7,7 @@
 namespace cddmsl {
 unsigned long long g_launch_count = 0;
 int tune_roi(const char* key, int value);
+extern int g_head_tc;
 
 int sm_count() {
   static int cached = 0;
@@ -37,4 +38,10 @@ extern "C" const char* cddmsl_error_string(int code) {
 }
 
 // Internal tuning hook used by bench sweeps (not part of the reference-facing surface).
-extern "C" int cddmsl_tune(const char* key, int value) { return cddmsl::tune_roi(key, value); }
+extern "C" int cddmsl_tune(const char* key, int value) {
+  if (!strcmp(key, "head_tc")) {
+    cddmsl::g_head_tc = value;
+    return 1;
+  }
+  return cddmsl::tune_roi(key, value);
+}

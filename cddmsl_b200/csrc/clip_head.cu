@@ -280,6 +280,13 @@ static HeadWs head_carve(void* base, int R, int D, int K) {
   return w;
 }
 
+bool clip_head_tc_eligible(int R, int D, int K);
+size_t clip_head_tc_workspace_bytes(int R, int D, int K);
+int clip_head_tc_run(int op, const float* x, const float* w, const float* w_bg, const int64_t* gt,
+                     const float* dscores, int R, int D, int K, float temperature, int loss_mode, float gamma,
+                     float bg_weight, const float* grad_scale, int strict_nan, float* scores, float* loss, float* dx,
+                     int32_t* stats, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 static int head_launch(HeadArgs a, const float* w, const float* w_bg, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream, float* loss) {
   if (a.R < 0 || a.D <= 0 || a.K < 0 || (a.D & 3)) return CDDMSL_EINVAL;
@@ -301,6 +308,12 @@ static int head_launch(HeadArgs a, const float* w, const float* w_bg, void* work
     }
   }
   if (a.R == 0) return CDDMSL_OK;
+  // LVIS-scale vocabularies: the logits are a dense contraction -> tcgen05 path (clip_head_tc.cuh)
+  if (a.op != HEAD_OP_SCORES_BWD && clip_head_tc_eligible(a.R, a.D, a.K) &&
+      workspace_bytes >= clip_head_tc_workspace_bytes(a.R, a.D, a.K))
+    return clip_head_tc_run(a.op == HEAD_OP_SCORES ? 0 : 1, a.x, w, w_bg, a.gt, nullptr, a.R, a.D, a.K, 1.f / a.inv_T,
+                            a.loss_mode, a.gamma, a.bg_weight, a.grad_scale, a.strict_nan, a.scores, loss, a.dx,
+                            a.stats, workspace, workspace_bytes, stream);
   clip_head_prep_kernel<<<ceil_div((a.K + 1) * 32, 256), 256, 0, stream>>>(w, w_bg, a.K, a.D, ws.wall);
   count_launch();
   a.norm_host = (float)a.R;
@@ -324,10 +337,15 @@ static int head_launch(HeadArgs a, const float* w, const float* w_bg, void* work
 
 }  // namespace cddmsl
 
+#include "clip_head_tc.cuh"
+
 using namespace cddmsl;
 
 extern "C" size_t cddmsl_clip_head_workspace_bytes(int R, int D, int K) {
-  return head_carve(nullptr, R > 0 ? R : 0, D, K).total;
+  const int r = R > 0 ? R : 0;
+  size_t b = head_carve(nullptr, r, D, K).total;
+  if (r > 0 && clip_head_tc_eligible(r, D, K)) b = b > clip_head_tc_workspace_bytes(r, D, K) ? b : clip_head_tc_workspace_bytes(r, D, K);
+  return b;
 }
 
 extern "C" int cddmsl_clip_head_scores(const float* x, const float* w, const float* w_bg, int R, int D, int K,

@@ -139,11 +139,23 @@ def test_unfused_path_scores_autograd():
     _close(xx.grad.cpu().numpy(), xr.grad.numpy(), 1e-4)
 
 
-def test_large_vocabulary_generic_kernel():
-    """LVIS-scale vocabulary (K=1203) through the generic CUDA-core kernel at a row count the CPU oracle
-    finishes quickly."""
+@pytest.mark.parametrize("path,r,dim,k", [("cuda_cores", 2048, 1024, 1203), ("tcgen05", 2048, 1024, 1203),
+                                          ("tcgen05", 130, 64, 259), ("tcgen05", 700, 96, 1203)])
+def test_large_vocabulary(path, r, dim, k):
+    """LVIS-scale vocabulary (BASELINE.json configs[3]: 1203 concepts) at a row count the CPU oracle finishes
+    quickly, through both implementations: the generic warp-per-row kernel and the tcgen05 3xTF32 GEMM path
+    (ragged M, N and a K that is not a multiple of the tile)."""
+    from cddmsl_b200 import _lib
+
+    _lib.tune("head_tc", 0 if path == "cuda_cores" else 1)
+    try:
+        _large_vocab_case(r, dim, k)
+    finally:
+        _lib.tune("head_tc", 2)
+
+
+def _large_vocab_case(r, dim, k):
     g = synth.generator(3)
-    r, dim, k = 2048, 1024, 1203
     x = torch.randn(r, dim, generator=g)
     w = torch.randn(k, dim, generator=g)
     gt = torch.randint(0, k + 1, (r,), generator=g)
