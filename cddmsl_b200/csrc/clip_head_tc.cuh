@@ -5,7 +5,7 @@
 // contraction: [R x 1024] . [1024 x 1204] forward and [R x 1204] . [1204 x 1024] for dx — 3.2e11 flop at R = 65536,
 // arithmetic intensity ~400 flop/B, i.e. tensor-core bound.  The parity bar (1e-5 relative on logits
 // that are cosines / 0.01) rules out plain TF32 (10-bit mantissa -> ~1e-3), so every operand is split
-//     x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly representable in TF32),  lo = x - hi
+//     x = hi + lo,  hi = RN_tf32(x),  lo = RN_tf32(x - hi)   (|x - hi - lo| <= 2^-24 |x|)
 // and each K-slice issues three tcgen05.mma: hi.hi + hi.lo + lo.hi, accumulated in fp32 in TMEM (error ~2^-22).
 //
 // One kernel, C[M x N] = A[M x K] . B[N x K]^T, both operands K-major fp32:
@@ -34,7 +34,7 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;  // BK * 4 B = 128 B = one s
 constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;     // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;    // A hi, A lo, B hi, B lo
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 split (2-5 also run the epilogue)
 constexpr uint32_t TC_TMEM_COLS = 128;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------
@@ -99,6 +99,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// round-to-nearest conversion to TF32 (result is an fp32 bit pattern with the low 13 mantissa bits clear)
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // K-major, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (1), descriptor version 1.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
@@ -137,7 +144,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 4);   // one arrival per split warp
+      mbar_init(&conv_bar[s], 8);   // one arrival per split warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
@@ -192,39 +199,45 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else {
     // ===================== split (hi / lo) warps, then epilogue =====================
-    const int t = threadIdx.x - 64;  // 0..127: row of the A tile and of the B tile
+    // 256 threads: thread u < 128 rewrites row u of the A tile, thread u >= 128 row u-128 of the B tile
+    const int u = threadIdx.x - 64;
+    const int t = u & 127;
+    const int op = u >> 7;
     float ss = 0.f;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % TC_STAGES;
       const uint32_t ph = (kb / TC_STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
+      float4* hi = reinterpret_cast<float4*>(st + (size_t)op * 2 * TC_TILE_BYTES) + t * 8;
+      float4* lo = reinterpret_cast<float4*>(st + (size_t)(op * 2 + 1) * TC_TILE_BYTES) + t * 8;
+      float4 v[8];
 #pragma unroll
-      for (int op = 0; op < 2; ++op) {
-        float4* hi = reinterpret_cast<float4*>(st + (size_t)op * 2 * TC_TILE_BYTES) + t * 8;
-        float4* lo = reinterpret_cast<float4*>(st + (size_t)(op * 2 + 1) * TC_TILE_BYTES) + t * 8;
+      for (int c = 0; c < 8; ++c) v[c] = hi[c ^ (t & 7)];  // swizzled visiting order: conflict-free per quarter warp
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int cc = c ^ (t & 7);  // visit the 16-byte chunks in swizzled order: conflict-free across a quarter warp
-          const float4 v = hi[cc];
-          if (op == 0) ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          l.x = v.x - h.x;
-          l.y = v.y - h.y;
-          l.z = v.z - h.z;
-          l.w = v.w - h.w;
-          hi[cc] = h;
-          lo[cc] = l;
-        }
+      for (int c = 0; c < 8; ++c) {
+        const int cc = c ^ (t & 7);
+        if (op == 0) ss = fmaf(v[c].x, v[c].x, fmaf(v[c].y, v[c].y, fmaf(v[c].z, v[c].z, fmaf(v[c].w, v[c].w, ss))));
+        // hi = RN_tf32(v); lo = RN_tf32(v - hi): |v - hi - lo| <= 2^-24 |v| (a truncating split loses 2^-21)
+        float4 h, l;
+        h.x = to_tf32(v[c].x);
+        h.y = to_tf32(v[c].y);
+        h.z = to_tf32(v[c].z);
+        h.w = to_tf32(v[c].w);
+        l.x = to_tf32(v[c].x - h.x);
+        l.y = to_tf32(v[c].y - h.y);
+        l.z = to_tf32(v[c].z - h.z);
+        l.w = to_tf32(v[c].w - h.w);
+        hi[cc] = h;
+        lo[cc] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&conv_bar[s]);
     }
+    if (op == 1) {
+      // B-side split warps have no epilogue work
+    } else {
     ss_s[t] = ss;
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four split/epilogue warps only
     // ---- epilogue: a warp may touch TMEM lanes [32 * (warp % 4), +32)
@@ -275,6 +288,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
   }
   __syncthreads();
   if (warp == 1) {
