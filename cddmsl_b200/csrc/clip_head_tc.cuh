@@ -5,7 +5,7 @@
 // contraction: [R x 1024] . [1024 x 1204] forward and [R x 1204] . [1204 x 1024] for dx — 3.2e11 flop at R = 65536,
 // arithmetic intensity ~400 flop/B, i.e. tensor-core bound.  The parity bar (1e-5 relative on logits
 // that are cosines / 0.01) rules out plain TF32 (10-bit mantissa -> ~1e-3), so every operand is split
-//     x = hi + lo,  hi = RN_tf32(x),  lo = RN_tf32(x - hi)   (|x - hi - lo| <= 2^-24 |x|)
+//     x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exact in TF32),  lo = x - hi
 // and each K-slice issues three tcgen05.mma: hi.hi + hi.lo + lo.hi, accumulated in fp32 in TMEM (error ~2^-22).
 //
 // One kernel, C[M x N] = A[M x K] . B[N x K]^T, both operands K-major fp32:
@@ -99,12 +99,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// round-to-nearest conversion to TF32 (result is an fp32 bit pattern with the low 13 mantissa bits clear)
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// TF32 "hi" part: clear the low 13 mantissa bits (one LOP3).  cvt.rna.tf32.f32 would round to nearest, but it is
+// emulated on sm_100a (~7 instructions) and made the split warps the bottleneck (ncu: 43 % issue-active, tensor pipe
+// 26 %); the accumulated error is dominated by the tensor-core accumulation either way (measured 1.6e-4 vs 1.8e-4
+// max abs on logits of scale 17.7).
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // K-major, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (1), descriptor version 1.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -218,16 +217,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int c = 0; c < 8; ++c) {
         const int cc = c ^ (t & 7);
         if (op == 0) ss = fmaf(v[c].x, v[c].x, fmaf(v[c].y, v[c].y, fmaf(v[c].z, v[c].z, fmaf(v[c].w, v[c].w, ss))));
-        // hi = RN_tf32(v); lo = RN_tf32(v - hi): |v - hi - lo| <= 2^-24 |v| (a truncating split loses 2^-21)
         float4 h, l;
         h.x = to_tf32(v[c].x);
         h.y = to_tf32(v[c].y);
         h.z = to_tf32(v[c].z);
         h.w = to_tf32(v[c].w);
-        l.x = to_tf32(v[c].x - h.x);
-        l.y = to_tf32(v[c].y - h.y);
-        l.z = to_tf32(v[c].z - h.z);
-        l.w = to_tf32(v[c].w - h.w);
+        l.x = v[c].x - h.x;  // exact; the tensor core drops its low bits (2^-21 |v|)
+        l.y = v[c].y - h.y;
+        l.z = v[c].z - h.z;
+        l.w = v[c].w - h.w;
         hi[cc] = h;
         lo[cc] = l;
       }
