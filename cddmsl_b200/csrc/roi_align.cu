@@ -415,10 +415,10 @@ extern int g_fwd_cpl, g_bwd_cpl;  // channels-last fast path (roi_align_cl.cu) f
 
 bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW);
 size_t roi_cl_workspace_bytes(int N, int C, int H, int W);
-int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, float scale,
-                     int sampling_ratio, int aligned, float* ft, cudaStream_t stream);
-int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, float scale,
-                     int sampling_ratio, int aligned, float* gt, cudaStream_t stream);
+int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, float* ft, cudaStream_t stream);
+int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, float* gt, cudaStream_t stream);
 
 int tune_roi(const char* key, int value) {
   if (!strcmp(key, "roi_fwd_smem_kb")) g_fwd_smem_kb = value;
@@ -456,8 +456,8 @@ extern "C" int cddmsl_roi_align_fwd(const float* in, const float* rois, float* o
   if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return CDDMSL_EALIGN;
   if (g_use_cl && roi_cl_eligible(N, C, H, W, PH, PW) && workspace &&
       workspace_bytes >= roi_cl_workspace_bytes(N, C, H, W) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
-    return roi_align_fwd_cl(in, rois, out, N, C, H, W, R, spatial_scale, sampling_ratio, aligned, (float*)workspace,
-                            stream);
+    return roi_align_fwd_cl(in, rois, out, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned,
+                            (float*)workspace, stream);
   const int CC = min(g_fwd_cc, C);
   const int nchunks = ceil_div(C, CC);
   if ((long long)R * nchunks > 0x7fffffffLL) return CDDMSL_EINVAL;
@@ -504,8 +504,8 @@ extern "C" int cddmsl_roi_align_bwd(const float* gout, const float* rois, float*
   if ((reinterpret_cast<uintptr_t>(gout) & 15) != 0) return CDDMSL_EALIGN;
   if (g_use_cl && roi_cl_eligible(N, C, H, W, PH, PW) && workspace &&
       workspace_bytes >= roi_cl_workspace_bytes(N, C, H, W) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
-    return roi_align_bwd_cl(gout, rois, gin, N, C, H, W, R, spatial_scale, sampling_ratio, aligned, (float*)workspace,
-                            stream);
+    return roi_align_bwd_cl(gout, rois, gin, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned,
+                            (float*)workspace, stream);
   CDDMSL_CUDA(cudaMemsetAsync(gin, 0, gin_bytes, stream));
   const int CC = min(g_bwd_cc, C);
   const int nchunks = ceil_div(C, CC);

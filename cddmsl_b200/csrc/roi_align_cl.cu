@@ -75,16 +75,26 @@ __device__ __forceinline__ TapE make_tap_entry(float start, float bin, int p, in
   return e;
 }
 
+__device__ __forceinline__ TapE null_tap() {
+  TapE e;
+  e.lo = -1;
+  e.hi = 0;
+  e.wl = e.wh = 0.f;
+  return e;
+}
+
+// Tables cover PE = P rounded up to even bins (rows / columns are processed in pairs); a bin >= P contributes nothing.
 template <int P, int NT>
 __device__ __forceinline__ void build_tables(TapE* xtab, TapE* ytab, const RoiGeom& g, int H, int W) {
-  for (int t = threadIdx.x; t < P * g.gw; t += NT) {
+  constexpr int PE = (P + 1) & ~1;
+  for (int t = threadIdx.x; t < PE * g.gw; t += NT) {
     const int p = t / g.gw, i = t - p * g.gw;
-    xtab[t] = make_tap_entry(g.sw, g.bw, p, i, g.gw, W, g.inv_count);
+    xtab[t] = p < P ? make_tap_entry(g.sw, g.bw, p, i, g.gw, W, g.inv_count) : null_tap();
   }
   if (ytab) {
-    for (int t = threadIdx.x; t < P * g.gh; t += NT) {
+    for (int t = threadIdx.x; t < PE * g.gh; t += NT) {
       const int p = t / g.gh, i = t - p * g.gh;
-      ytab[t] = make_tap_entry(g.sh, g.bh, p, i, g.gh, H, 1.f);
+      ytab[t] = p < P ? make_tap_entry(g.sh, g.bh, p, i, g.gh, H, 1.f) : null_tap();
     }
   }
 }
@@ -250,8 +260,17 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
     for (int k = 0; k < CPL; ++k) {
       if (k < nch) {
         float* o = orow + k * 32 * P * P;
-        *reinterpret_cast<float2*>(o + pw) = make_float2(sa0.v[k], sa1.v[k]);
-        *reinterpret_cast<float2*>(o + P + pw) = make_float2(sb0.v[k], sb1.v[k]);
+        if (P % 2 == 0) {
+          *reinterpret_cast<float2*>(o + pw) = make_float2(sa0.v[k], sa1.v[k]);
+          *reinterpret_cast<float2*>(o + P + pw) = make_float2(sb0.v[k], sb1.v[k]);
+        } else {  // odd pooled size (7x7): rows are not 8-byte aligned and the padded bin / row does not exist
+          o[pw] = sa0.v[k];
+          if (pw + 1 < P) o[pw + 1] = sa1.v[k];
+          if (row_a + 1 < P) {
+            o[P + pw] = sb0.v[k];
+            if (pw + 1 < P) o[P + pw + 1] = sb1.v[k];
+          }
+        }
       }
     }
   }
@@ -278,15 +297,15 @@ __device__ void fwd_direct_any(const float* __restrict__ in, float* __restrict__
 }
 
 template <int P, int CPL>
-__global__ void __launch_bounds__((P / 2) * 32, 4)
+__global__ void __launch_bounds__(((P + 1) / 2) * 32, 4)
 roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ in_nchw,
                         const float* __restrict__ rois, float* __restrict__ out, int N, int C, int H, int W, int R,
                         float scale, int sampling_ratio, int aligned, int ngroups) {
-  constexpr int NW = P / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL;
+  constexpr int NW = (P + 1) / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL, PE = (P + 1) & ~1;
   extern __shared__ __align__(128) float dyn_smem[];
   float* O_s = dyn_smem;                                        // [GC][PER]
-  TapE* xtab = reinterpret_cast<TapE*>(O_s + GC * PER);         // [P * kMaxG]
-  TapE* ytab = xtab + P * kMaxG;
+  TapE* xtab = reinterpret_cast<TapE*>(O_s + GC * PER);         // [PE * kMaxG]
+  TapE* ytab = xtab + PE * kMaxG;
   const int r = blockIdx.x / ngroups;
   const int c0 = (blockIdx.x - r * ngroups) * GC;
   const int nc = min(GC, C - c0);
@@ -320,14 +339,21 @@ roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ 
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(O_s);
-    const uint32_t bytes = (uint32_t)(nc * PER) * 4u;
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_tile), "r"(s), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    // the CTA may retire once the copy engine has READ the tile; the global writes complete on their own
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  // the bulk copy needs a 16-byte aligned destination and size (always true for 14x14; for 7x7 when the tile
+  // starts at a multiple of 4 channels)
+  const bool bulk_ok = ((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_tile) & 15) == 0);
+  if (bulk_ok) {
+    if (threadIdx.x == 0) {
+      const uint32_t s = (uint32_t)__cvta_generic_to_shared(O_s);
+      const uint32_t bytes = (uint32_t)(nc * PER) * 4u;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_tile), "r"(s), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // the CTA may retire once the copy engine has READ the tile; the global writes complete on their own
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    for (int e = threadIdx.x; e < nc * PER; e += NT) out_tile[e] = O_s[e];
   }
 }
 
@@ -435,7 +461,7 @@ __device__ __forceinline__ void bwd_flush(float* __restrict__ base, unsigned xb,
 template <int P, bool GH1, int CPL>
 __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* __restrict__ xtab,
                                          const YSlots* __restrict__ slots, int gw, int gh, int W, int C,
-                                         const float* __restrict__ grow, int nch) {
+                                         const float* __restrict__ grow, int nch, bool row_b_exists) {
   YSlots s1;
   if (GH1) s1 = slots[0];
   const unsigned Cb = (unsigned)C * 4u;
@@ -448,8 +474,15 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
       const float* gq = grow + (q < nch ? q : 0) * 32 * P * P;
-      ga[q] = *reinterpret_cast<const float2*>(gq + pw);
-      gb[q] = *reinterpret_cast<const float2*>(gq + P + pw);
+      if (P % 2 == 0) {
+        ga[q] = *reinterpret_cast<const float2*>(gq + pw);
+        gb[q] = *reinterpret_cast<const float2*>(gq + P + pw);
+      } else {  // odd pooled size: unaligned rows; the padded bin / row carries no gradient (its taps are null)
+        ga[q].x = gq[pw];
+        ga[q].y = pw + 1 < P ? gq[pw + 1] : 0.f;
+        gb[q].x = row_b_exists ? gq[P + pw] : 0.f;
+        gb[q].y = (row_b_exists && pw + 1 < P) ? gq[P + pw + 1] : 0.f;
+      }
     }
     for (int ix = 0; ix < gw; ++ix) {
       const TapE e = xt[ix];
@@ -469,14 +502,14 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
 }
 
 template <int P, int CPL>
-__global__ void __launch_bounds__((P / 2) * 32, 4)
+__global__ void __launch_bounds__(((P + 1) / 2) * 32, 4)
 roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict__ rois, float* __restrict__ gt, int N,
                         int C, int H, int W, int R, float scale, int sampling_ratio, int aligned, int ngroups) {
-  constexpr int NW = P / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL;
+  constexpr int NW = (P + 1) / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL, PE = (P + 1) & ~1;
   extern __shared__ __align__(128) float dyn_smem[];
-  float* G_s = dyn_smem;                                   // [GC][PER]
-  TapE* xtab = reinterpret_cast<TapE*>(G_s + GC * PER);    // [P * kMaxG]
-  YSlots* yslots = reinterpret_cast<YSlots*>(xtab + P * kMaxG);  // [NW][kMaxG]: [row pair][sample]
+  float* G_s = dyn_smem;                                   // [GC][PER] (+ pad to 16 B)
+  TapE* xtab = reinterpret_cast<TapE*>(G_s + ((GC * PER + 3) & ~3));    // [PE * kMaxG]
+  YSlots* yslots = reinterpret_cast<YSlots*>(xtab + PE * kMaxG);  // [NW][kMaxG]: [row pair][sample]
   const int r = blockIdx.x / ngroups;
   const int c0 = (blockIdx.x - r * ngroups) * GC;
   const int nc = min(GC, C - c0);
@@ -504,16 +537,20 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
     }
     return;
   }
-  {  // stage the contiguous grad tile (read once, streaming)
+  // stage the contiguous grad tile (read once, streaming)
+  if (((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_tile) & 15) == 0)) {
     const float4* s4 = reinterpret_cast<const float4*>(g_tile);
     float4* d4 = reinterpret_cast<float4*>(G_s);
     for (int e = threadIdx.x; e < nc * PER / 4; e += NT) d4[e] = __ldcs(s4 + e);
+  } else {
+    for (int e = threadIdx.x; e < nc * PER; e += NT) G_s[e] = __ldcs(g_tile + e);
   }
   build_tables<P, NT>(xtab, nullptr, g, H, W);
   for (int t = threadIdx.x; t < NW * g.gh; t += NT) {  // merged row slots of every (row pair, sample)
     const int j = t / g.gh, i = t - j * g.gh;
-    yslots[j * kMaxG + i] = make_slots(make_tap_entry(g.sh, g.bh, 2 * j, i, g.gh, H, 1.f),
-                                       make_tap_entry(g.sh, g.bh, 2 * j + 1, i, g.gh, H, 1.f), W * C);
+    yslots[j * kMaxG + i] =
+        make_slots(make_tap_entry(g.sh, g.bh, 2 * j, i, g.gh, H, 1.f),
+                   2 * j + 1 < P ? make_tap_entry(g.sh, g.bh, 2 * j + 1, i, g.gh, H, 1.f) : null_tap(), W * C);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -521,8 +558,9 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
   if (nch == 0) return;
   float* base = img + lane;
   const float* grow = G_s + lane * PER + (2 * warp) * P;
-  if (g.gh == 1) bwd_rows<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
-  else bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
+  const bool row_b_exists = 2 * warp + 1 < P;
+  if (g.gh == 1) bwd_rows<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
+  else bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,58 +568,62 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW) {
   (void)N;
-  return PH == 14 && PW == 14 && (long long)H * W * C < 0x7fffffffLL;
+  return PH == PW && (PH == 14 || PH == 7) && (long long)H * W * C < 0x7fffffffLL;
 }
 
 size_t roi_cl_workspace_bytes(int N, int C, int H, int W) { return align_up((size_t)N * C * H * W * 4, 256); }
 
 int g_fwd_cpl = 2, g_bwd_cpl = 2;  // channels per lane (tuning knobs "roi_fwd_cpl" / "roi_bwd_cpl")
 
-template <int CPL>
+template <int P, int CPL>
 static int launch_fwd_cl(const float* ft, const float* in, const float* rois, float* out, int N, int C, int H, int W,
                          int R, float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
+  constexpr int PE = (P + 1) & ~1, NW = (P + 1) / 2;
   const int ngroups = ceil_div(C, 32 * CPL);
   if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
-  const int smem = 32 * CPL * 196 * 4 + 2 * 14 * kMaxG * (int)sizeof(TapE);
-  auto k = roi_align_fwd_cl_kernel<14, CPL>;
+  const int smem = 32 * CPL * P * P * 4 + 2 * PE * kMaxG * (int)sizeof(TapE);
+  auto k = roi_align_fwd_cl_kernel<P, CPL>;
   cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ea != cudaSuccess) return (int)ea;
-  k<<<(unsigned)((long long)R * ngroups), 7 * 32, smem, stream>>>(ft, in, rois, out, N, C, H, W, R, scale,
-                                                                  sampling_ratio, aligned, ngroups);
+  k<<<(unsigned)((long long)R * ngroups), NW * 32, smem, stream>>>(ft, in, rois, out, N, C, H, W, R, scale,
+                                                                   sampling_ratio, aligned, ngroups);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-template <int CPL>
+template <int P, int CPL>
 static int launch_bwd_cl(const float* gout, const float* rois, float* gt, int N, int C, int H, int W, int R,
                          float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
+  constexpr int PE = (P + 1) & ~1, NW = (P + 1) / 2;
   const int ngroups = ceil_div(C, 32 * CPL);
   if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
-  const int smem = 32 * CPL * 196 * 4 + 14 * kMaxG * (int)sizeof(TapE) + 7 * kMaxG * (int)sizeof(YSlots);
-  auto k = roi_align_bwd_cl_kernel<14, CPL>;
+  const int smem = ((32 * CPL * P * P + 3) & ~3) * 4 + PE * kMaxG * (int)sizeof(TapE) + NW * kMaxG * (int)sizeof(YSlots);
+  auto k = roi_align_bwd_cl_kernel<P, CPL>;
   cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ea != cudaSuccess) return (int)ea;
-  k<<<(unsigned)((long long)R * ngroups), 7 * 32, smem, stream>>>(gout, rois, gt, N, C, H, W, R, scale,
-                                                                  sampling_ratio, aligned, ngroups);
+  k<<<(unsigned)((long long)R * ngroups), NW * 32, smem, stream>>>(gout, rois, gt, N, C, H, W, R, scale,
+                                                                   sampling_ratio, aligned, ngroups);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, float scale,
-                     int sampling_ratio, int aligned, float* ft, cudaStream_t stream) {
+int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, float* ft, cudaStream_t stream) {
   int rc = launch_transpose(in, ft, N, C, H * W, stream);  // NCHW -> NHWC
   if (rc) return rc;
-  return g_fwd_cpl == 2 ? launch_fwd_cl<2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
-                        : launch_fwd_cl<1>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
+  if (P == 7) return launch_fwd_cl<7, 2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
+  return g_fwd_cpl == 2 ? launch_fwd_cl<14, 2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+                        : launch_fwd_cl<14, 1>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
 }
 
-int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, float scale,
-                     int sampling_ratio, int aligned, float* gt, cudaStream_t stream) {
+int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, float* gt, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(gt, 0, (size_t)N * C * H * W * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
-  int rc = g_bwd_cpl == 2
-               ? launch_bwd_cl<2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
-               : launch_bwd_cl<1>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
+  int rc = P == 7 ? launch_bwd_cl<7, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+           : g_bwd_cpl == 2
+               ? launch_bwd_cl<14, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+               : launch_bwd_cl<14, 1>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
   if (rc) return rc;
   return launch_transpose(gt, gin, N, H * W, C, stream);  // NHWC -> NCHW (overwrites gin completely)
 }
