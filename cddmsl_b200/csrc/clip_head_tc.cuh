@@ -11,12 +11,12 @@
 // One kernel, C[M x N] = A[M x K] . B[N x K]^T, both operands K-major fp32:
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d of a [128 x 32] A tile and a [128 x 32] B tile per stage,
 //               128-byte swizzle, completion on an mbarrier
-//   warps 2-5   split: every thread rewrites its row of the freshly landed tiles in place (hi) and writes lo to a
+//   warps 2-9   split: every thread rewrites its row of the freshly landed tiles in place (hi) and writes lo to a
 //               second tile with the same swizzled addresses; in GEMM 1 they also accumulate |x|^2 per row
 //   warp 1      allocates TMEM, issues 3 x 4 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) per stage from
 //               shared-memory descriptors, tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld 32x32b, row scaling, global stores
-// 3 stages x 64 KB of shared memory, one CTA per SM, one output tile per CTA.
+//   warps 10-13 epilogue: tcgen05.ld 32x32b, row scaling, global stores
+// 3 stages x 64 KB of shared memory, one persistent CTA per SM, two TMEM accumulators (epilogue overlaps the next tile).
 //   GEMM 1 epilogue: logits = acc * (1 / max(|x|, eps)) / T  -> scores [R, K+1], norms
 //   (CUDA cores)   : row softmax / CE / focal factor / statistics, G = dL/dlogits, per-row scalars
 //   GEMM 2 epilogue: dx = acc * su[r] - x * sx[r]
@@ -34,8 +34,8 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;  // BK * 4 B = 128 B = one s
 constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;     // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;    // A hi, A lo, B hi, B lo
-constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 split (2-5 also run the epilogue)
-constexpr uint32_t TC_TMEM_COLS = 128;
+constexpr int TC_THREADS = 448;  // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 10-13 epilogue
+constexpr uint32_t TC_TMEM_COLS = 256;  // two 128-column fp32 accumulators
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,19 +126,23 @@ struct TcEpilogue {
   const float* sx;     // mode 1: per-row scale of x
 };
 
+// Persistent: each CTA walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that run
+// at the same time share their A rows in L2).  Three pipelines: smem stages (TMA -> split -> MMA -> TMA), two TMEM
+// accumulators (MMA <-> epilogue) so the epilogue of tile i overlaps the main loop of tile i+1, and the tile walk.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int K,
-                   TcEpilogue ep) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                   int K, TcEpilogue ep) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[TC_STAGES], conv_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
+  __shared__ uint64_t full_bar[TC_STAGES], conv_bar[TC_STAGES], empty_bar[TC_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float ss_s[TC_BM];
+  __shared__ float ss_s[2][TC_BM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int tiles_n = (N + TC_BN - 1) / TC_BN;
+  const int ntiles = tiles_n * ((M + TC_BM - 1) / TC_BM);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -146,7 +150,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&conv_bar[s], 8);   // one arrival per split warp
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it at the end
@@ -163,131 +170,154 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);  // first pass over the ring falls through (barrier parity starts at 0)
-        uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], 2 * TC_TILE_BYTES);
-        tma_load_2d(st, &map_a, kb * TC_BK, m0, &full_bar[s]);                      // A hi slot
-        tma_load_2d(st + 2 * TC_TILE_BYTES, &map_b, kb * TC_BK, n0, &full_bar[s]);  // B hi slot
+      int g = 0;  // k-blocks issued so far (ring position)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * TC_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % TC_STAGES;
+          const uint32_t ph = (g / TC_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);  // first pass over the ring falls through (barrier parity starts at 0)
+          uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], 2 * TC_TILE_BYTES);
+          tma_load_2d(st, &map_a, kb * TC_BK, m0, &full_bar[s]);                      // A hi slot
+          tma_load_2d(st + 2 * TC_TILE_BYTES, &map_b, kb * TC_BK, n0, &full_bar[s]);  // B hi slot
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % TC_STAGES;
-      const uint32_t ph = (kb / TC_STAGES) & 1;
-      mbar_wait(&conv_bar[s], ph);
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t st = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
-        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_TILE_BYTES);
-        const uint64_t b_hi = make_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = make_desc_sw128(st + 3 * TC_TILE_BYTES);
+      const uint32_t acc = tmem_base + (uint32_t)(buf * TC_BN);
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const int s = g % TC_STAGES;
+        const uint32_t ph = (g / TC_STAGES) & 1;
+        mbar_wait(&conv_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_TILE_BYTES);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * TC_TILE_BYTES),
+                         b_lo = make_desc_sw128(st + 3 * TC_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 B per K=8 step inside the swizzle row
-          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, kIdescTf32, (kb | k) != 0);
-          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, kIdescTf32, 1u);
-          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, kIdescTf32, 1u);
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 B per K=8 step inside the swizzle row
+            umma_tf32(acc, a_hi + adv, b_hi + adv, kIdescTf32, (kb | k) != 0);
+            umma_tf32(acc, a_hi + adv, b_lo + adv, kIdescTf32, 1u);
+            umma_tf32(acc, a_lo + adv, b_hi + adv, kIdescTf32, 1u);
+          }
+          umma_commit(&empty_bar[s]);                       // stage reusable once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&acc_full[buf]);  // accumulator complete
         }
-        umma_commit(&empty_bar[s]);                    // stage reusable once these MMAs have read it
-        if (kb == num_kb - 1) umma_commit(&accum_bar); // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
-  } else {
-    // ===================== split (hi / lo) warps, then epilogue =====================
+  } else if (warp < 10) {
+    // ===================== split (hi / lo) warps =====================
     // 256 threads: thread u < 128 rewrites row u of the A tile, thread u >= 128 row u-128 of the B tile
     const int u = threadIdx.x - 64;
     const int t = u & 127;
     const int op = u >> 7;
-    float ss = 0.f;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % TC_STAGES;
-      const uint32_t ph = (kb / TC_STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
-      uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
-      float4* hi = reinterpret_cast<float4*>(st + (size_t)op * 2 * TC_TILE_BYTES) + t * 8;
-      float4* lo = reinterpret_cast<float4*>(st + (size_t)(op * 2 + 1) * TC_TILE_BYTES) + t * 8;
-      float4 v[8];
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      float ss = 0.f;
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const int s = g % TC_STAGES;
+        const uint32_t ph = (g / TC_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
+        float4* hi = reinterpret_cast<float4*>(st + (size_t)op * 2 * TC_TILE_BYTES) + t * 8;
+        float4* lo = reinterpret_cast<float4*>(st + (size_t)(op * 2 + 1) * TC_TILE_BYTES) + t * 8;
+        float4 v[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = hi[c ^ (t & 7)];  // swizzled visiting order: conflict-free per quarter warp
+        for (int c = 0; c < 8; ++c) v[c] = hi[c ^ (t & 7)];  // swizzled visiting order: conflict-free per quarter warp
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int cc = c ^ (t & 7);
-        if (op == 0) ss = fmaf(v[c].x, v[c].x, fmaf(v[c].y, v[c].y, fmaf(v[c].z, v[c].z, fmaf(v[c].w, v[c].w, ss))));
-        float4 h, l;
-        h.x = to_tf32(v[c].x);
-        h.y = to_tf32(v[c].y);
-        h.z = to_tf32(v[c].z);
-        h.w = to_tf32(v[c].w);
-        l.x = v[c].x - h.x;  // exact; the tensor core drops its low bits (2^-21 |v|)
-        l.y = v[c].y - h.y;
-        l.z = v[c].z - h.z;
-        l.w = v[c].w - h.w;
-        hi[cc] = h;
-        lo[cc] = l;
+        for (int c = 0; c < 8; ++c) {
+          const int cc = c ^ (t & 7);
+          if (op == 0)
+            ss = fmaf(v[c].x, v[c].x, fmaf(v[c].y, v[c].y, fmaf(v[c].z, v[c].z, fmaf(v[c].w, v[c].w, ss))));
+          float4 h, l;
+          h.x = to_tf32(v[c].x);
+          h.y = to_tf32(v[c].y);
+          h.z = to_tf32(v[c].z);
+          h.w = to_tf32(v[c].w);
+          l.x = v[c].x - h.x;  // exact; the tensor core drops its low bits (2^-21 |v|)
+          l.y = v[c].y - h.y;
+          l.z = v[c].z - h.z;
+          l.w = v[c].w - h.w;
+          hi[cc] = h;
+          lo[cc] = l;
+        }
+        // |x|^2 of the tile's rows travels with the last stage: written before the arrive the MMA (and through its
+        // commit the epilogue) synchronises on.  The slot is free again long before tile it+2 gets here: its MMAs
+        // cannot start until the epilogue of tile `it` has released the accumulator.
+        if (op == 0 && kb == num_kb - 1) ss_s[it & 1][t] = ss;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[s]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&conv_bar[s]);
     }
-    if (op == 1) {
-      // B-side split warps have no epilogue work
-    } else {
-    ss_s[t] = ss;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four split/epilogue warps only
-    // ---- epilogue: a warp may touch TMEM lanes [32 * (warp % 4), +32)
-    mbar_wait(&accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  } else {
+    // ===================== epilogue warps (10-13): a warp may touch TMEM lanes [32 * (warp % 4), +32)
     const int lg = warp & 3;
     const int row_in_tile = lg * 32 + lane;
-    const int row = m0 + row_in_tile;
-    float rs = 0.f, rx = 0.f;
-    if (ep.mode == 0) {
-      const float nrm = sqrtf(ss_s[row_in_tile]);
-      rs = ep.inv_T / fmaxf(nrm, 1e-12f);
-      if (row < M && blockIdx.x == 0) ep.norms[row] = nrm;
-    } else if (row < M) {
-      rs = ep.su[row];
-      rx = ep.sx[row];
-    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * TC_BN;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + row_in_tile;
+      float rs = 0.f, rx = 0.f;
+      if (ep.mode == 0) {
+        const float nrm = sqrtf(ss_s[buf][row_in_tile]);
+        rs = ep.inv_T / fmaxf(nrm, 1e-12f);
+        if (row < M && n0 == 0) ep.norms[row] = nrm;
+      } else if (row < M) {
+        rs = ep.su[row];
+        rx = ep.sx[row];
+      }
 #pragma unroll 1
-    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
-      if (row < M) {
-        const int col0 = n0 + c0;
-        float* o = ep.out + (size_t)row * ep.ldo + col0;
-        const float* xr = ep.mode == 1 ? ep.x + (size_t)row * ep.ldo + col0 : nullptr;
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * TC_BN + c0), r);
+        if (row < M) {
+          const int col0 = n0 + c0;
+          float* o = ep.out + (size_t)row * ep.ldo + col0;
+          const float* xr = ep.mode == 1 ? ep.x + (size_t)row * ep.ldo + col0 : nullptr;
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          if (col0 + q + 3 < ep.n_valid) {
-            float4 v = make_float4(__uint_as_float(r[q]) * rs, __uint_as_float(r[q + 1]) * rs,
-                                   __uint_as_float(r[q + 2]) * rs, __uint_as_float(r[q + 3]) * rs);
-            if (ep.mode == 1) {
-              const float4 xv = *reinterpret_cast<const float4*>(xr + q);
-              v.x = fmaf(-xv.x, rx, v.x);
-              v.y = fmaf(-xv.y, rx, v.y);
-              v.z = fmaf(-xv.z, rx, v.z);
-              v.w = fmaf(-xv.w, rx, v.w);
-            }
-            *reinterpret_cast<float4*>(o + q) = v;
-          } else {
-            for (int e = 0; e < 4; ++e)
-              if (col0 + q + e < ep.n_valid) {
-                float v = __uint_as_float(r[q + e]) * rs;
-                if (ep.mode == 1) v = fmaf(-xr[q + e], rx, v);
-                o[q + e] = v;
+          for (int q = 0; q < 32; q += 4) {
+            if (col0 + q + 3 < ep.n_valid) {
+              float4 v = make_float4(__uint_as_float(r[q]) * rs, __uint_as_float(r[q + 1]) * rs,
+                                     __uint_as_float(r[q + 2]) * rs, __uint_as_float(r[q + 3]) * rs);
+              if (ep.mode == 1) {
+                const float4 xv = *reinterpret_cast<const float4*>(xr + q);
+                v.x = fmaf(-xv.x, rx, v.x);
+                v.y = fmaf(-xv.y, rx, v.y);
+                v.z = fmaf(-xv.z, rx, v.z);
+                v.w = fmaf(-xv.w, rx, v.w);
               }
+              *reinterpret_cast<float4*>(o + q) = v;
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (col0 + q + e < ep.n_valid) {
+                  float v = __uint_as_float(r[q + e]) * rs;
+                  if (ep.mode == 1) v = fmaf(-xr[q + e], rx, v);
+                  o[q + e] = v;
+                }
+            }
           }
         }
       }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);  // this warp's quarter of the accumulator is drained
     }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -467,8 +497,8 @@ static int launch_gemm(const float* A, int M, int lda, const float* B, int N, in
   const int smem = TC_STAGES * TC_STAGE_BYTES + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(ceil_div(N, TC_BN), ceil_div(M, TC_BM));
-  gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, stream>>>(ma, mb, M, K, ep);
+  const int ntiles = ceil_div(N, TC_BN) * ceil_div(M, TC_BM);
+  gemm_tf32x3_kernel<<<min(ntiles, sm_count()), TC_THREADS, smem, stream>>>(ma, mb, M, N, K, ep);
   count_launch();
   return (int)cudaGetLastError();
 }
