@@ -49,52 +49,91 @@ def parse():
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled every 100 ms DURING the timed region, through NVML in-process
+    (nvidia_ml_py).  Spawning `nvidia-smi -lms` instead costs an NVML initialisation inside the timed region, which
+    showed up as single 20+ ms stalls of whatever kernel was running; `nvidia-smi` is only the fallback."""
+    NAMES = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+             "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self.stop_flag, self.thread, self.h = index, [], False, None, None
+        self.recording = False
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML enumerates physical devices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                if self.recording:
+                    self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def warm(self):
+        """Start polling BEFORE the warm-up steps: the first NVML queries of a process take the driver lock for tens
+        of milliseconds (seen as one 20-100 ms stall of the kernel launches); only samples taken between start()
+        and stop() are kept."""
+        self.recording = False
+        if self.nvml is not None and self.thread is None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.warm()
+        self.recording = True
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
+        if self.nvml is None:
+            return self._nvidia_smi_once()
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return self._nvidia_smi_once()
+        sm = [s[0] for s in self.samples]
+        reasons = set()
+        for _, _, r in self.samples:
+            for nm, bit in self.NAMES.items():
+                if r & bit:
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.max_sm,
+                "power_w_max": max(s[1] for s in self.samples), "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvml"}
+
+    def _nvidia_smi_once(self):
+        try:
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "power_w_max": float(f[2]), "samples": 1,
+                    "reasons": [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")],
+                    "source": "nvidia-smi after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
 
 
 # -------------------------------------------------------------------------------------- reference arm
@@ -230,10 +269,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    barrier()
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.warm()
+    res = None
+    for _ in range(max(args.warmup, 3)):
+        # keep the previous step's results alive exactly like the timed loop does: otherwise the caching allocator
+        # meets its steady-state footprint (two live gradient maps) only at timed step 1 and stalls the host in
+        # cudaMalloc for 10-100 ms (measured)
+        res = device_step()
+    barrier()
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
@@ -250,7 +295,10 @@ def run_ours(args):
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    seg = [statistics.mean(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)) for j in range(4)]
+    seg_all = [[ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)] for j in range(4)]
+    seg = [statistics.mean(v) for v in seg_all]
+    seg_minmax = [(min(v), statistics.median(v), max(v)) for v in seg_all]
+    mstats = torch.cuda.memory_stats(dev)
     losses = [float(v) for v in res[:3]]
 
     # ---------------- end to end through the reference-shaped API, host buffers in and out every step
@@ -356,7 +404,11 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bytes_roi = R * (4 * C * P * P + 20) + N * C * Hf * Wf * 4
     names = ["roi_align_fwd", "clip_head_fwd_bwd", "align_loss_x2_fwd_bwd", "roi_align_bwd"]
-    kern = {n: {"ms": round(seg[j], 4)} for j, n in enumerate(names)}
+    kern = {n: {"ms": round(seg[j], 4), "ms_min_med_max": [round(x, 4) for x in seg_minmax[j]]}
+            for j, n in enumerate(names)}
+    kern["allocator"] = {"num_device_alloc": int(mstats.get("num_device_alloc", 0)),
+                         "num_alloc_retries": int(mstats.get("num_alloc_retries", 0)),
+                         "reserved_GB": round(mstats.get("reserved_bytes.all.peak", 0) / 1e9, 2)}
     kern["roi_align_fwd"].update(gbs=bytes_roi / (seg[0] * 1e-3) / 1e9, bytes=bytes_roi)
     kern["roi_align_bwd"].update(gbs=bytes_roi / (seg[3] * 1e-3) / 1e9, bytes=bytes_roi)
     head_bytes = R * (2 * cfg.emb_dim * 4 + 8)

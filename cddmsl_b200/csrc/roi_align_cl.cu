@@ -300,60 +300,65 @@ template <int P, int CPL>
 __global__ void __launch_bounds__(((P + 1) / 2) * 32, 4)
 roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ in_nchw,
                         const float* __restrict__ rois, float* __restrict__ out, int N, int C, int H, int W, int R,
-                        float scale, int sampling_ratio, int aligned, int ngroups) {
+                        float scale, int sampling_ratio, int aligned, int ngroups, int gpc) {
   constexpr int NW = (P + 1) / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL, PE = (P + 1) & ~1;
   extern __shared__ __align__(128) float dyn_smem[];
   float* O_s = dyn_smem;                                        // [GC][PER]
   TapE* xtab = reinterpret_cast<TapE*>(O_s + GC * PER);         // [PE * kMaxG]
   TapE* ytab = xtab + PE * kMaxG;
+  // One CTA = one RoI x `gpc` consecutive 64-channel groups: geometry and tap tables are built once and reused.
   const int r = blockIdx.x / ngroups;
-  const int c0 = (blockIdx.x - r * ngroups) * GC;
-  const int nc = min(GC, C - c0);
+  const int cbeg = (blockIdx.x - r * ngroups) * (GC * gpc);
+  const int cend = min(C, cbeg + GC * gpc);
   const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
-  float* out_tile = out + ((size_t)r * C + c0) * PER;
   if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) {
-    for (int e = threadIdx.x; e < nc * PER; e += NT) out_tile[e] = 0.f;
+    float* o = out + ((size_t)r * C + cbeg) * PER;
+    for (int e = threadIdx.x; e < (cend - cbeg) * PER; e += NT) o[e] = 0.f;
     return;
   }
   if (g.gw > kMaxG || g.gh > kMaxG) {  // more samples per bin than the tables hold: reference-order loop
-    fwd_direct_any(in_nchw, out + (size_t)r * C * PER, c0, nc, C, H, W, P, P, g, NT);
+    fwd_direct_any(in_nchw, out + (size_t)r * C * PER, cbeg, cend - cbeg, C, H, W, P, P, g, NT);
     return;
   }
   build_tables<P, NT>(xtab, ytab, g, H, W);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // channels of this lane: c0 + lane + 32k.  A ragged last group clamps the LOAD channel (so surplus lanes read
-  // valid memory) and masks the store.
-  const int nch = lane < nc ? min(CPL, (nc - lane + 31) / 32) : 0;
-  if (nch > 0) {
-    // loads of channel k >= nch would run past C: fold them onto channel 0 of the lane by using CPL' = nch
-    const float* base = ft + (size_t)g.batch * H * W * C + c0 + lane;
-    float* orow = O_s + lane * PER + (2 * warp) * P;
-    if (nch == CPL) {
-      if (g.gh == 1) fwd_rows<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
-      else if (g.gh == 2) fwd_rows<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
-      else fwd_rows<P, 0, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
+  for (int c0 = cbeg; c0 < cend; c0 += GC) {
+    const int nc = min(GC, cend - c0);
+    float* out_tile = out + ((size_t)r * C + c0) * PER;
+    // channels of this lane: c0 + lane + 32k; a ragged last group masks the missing ones
+    const int nch = lane < nc ? min(CPL, (nc - lane + 31) / 32) : 0;
+    if (nch > 0) {
+      const float* base = ft + (size_t)g.batch * H * W * C + c0 + lane;
+      float* orow = O_s + lane * PER + (2 * warp) * P;
+      if (nch == CPL) {
+        if (g.gh == 1) fwd_rows<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
+        else if (g.gh == 2) fwd_rows<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
+        else fwd_rows<P, 0, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, nch);
+      } else {
+        fwd_rows<P, 0, 1>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 1);  // ragged tail: one channel
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // the bulk copy needs a 16-byte aligned destination and size (always true for 14x14; for 7x7 when the tile
+    // starts at a multiple of 4 channels)
+    const bool bulk_ok = ((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_tile) & 15) == 0);
+    if (bulk_ok) {
+      if (threadIdx.x == 0) {
+        const uint32_t s = (uint32_t)__cvta_generic_to_shared(O_s);
+        const uint32_t bytes = (uint32_t)(nc * PER) * 4u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_tile), "r"(s),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // O_s may be rewritten (or the CTA retire) once the copy engine has READ the tile
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
     } else {
-      fwd_rows<P, 0, 1>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 1);  // ragged tail: one channel
+      for (int e = threadIdx.x; e < nc * PER; e += NT) out_tile[e] = O_s[e];
     }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  // the bulk copy needs a 16-byte aligned destination and size (always true for 14x14; for 7x7 when the tile
-  // starts at a multiple of 4 channels)
-  const bool bulk_ok = ((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_tile) & 15) == 0);
-  if (bulk_ok) {
-    if (threadIdx.x == 0) {
-      const uint32_t s = (uint32_t)__cvta_generic_to_shared(O_s);
-      const uint32_t bytes = (uint32_t)(nc * PER) * 4u;
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_tile), "r"(s), "r"(bytes)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      // the CTA may retire once the copy engine has READ the tile; the global writes complete on their own
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-  } else {
-    for (int e = threadIdx.x; e < nc * PER; e += NT) out_tile[e] = O_s[e];
+    if (c0 + GC < cend) __syncthreads();  // next group overwrites the tile
   }
 }
 
@@ -504,21 +509,21 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
 template <int P, int CPL>
 __global__ void __launch_bounds__(((P + 1) / 2) * 32, 4)
 roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict__ rois, float* __restrict__ gt, int N,
-                        int C, int H, int W, int R, float scale, int sampling_ratio, int aligned, int ngroups) {
+                        int C, int H, int W, int R, float scale, int sampling_ratio, int aligned, int ngroups, int gpc) {
   constexpr int NW = (P + 1) / 2, NT = NW * 32, PER = P * P, GC = 32 * CPL, PE = (P + 1) & ~1;
   extern __shared__ __align__(128) float dyn_smem[];
   float* G_s = dyn_smem;                                   // [GC][PER] (+ pad to 16 B)
   TapE* xtab = reinterpret_cast<TapE*>(G_s + ((GC * PER + 3) & ~3));    // [PE * kMaxG]
   YSlots* yslots = reinterpret_cast<YSlots*>(xtab + PE * kMaxG);  // [NW][kMaxG]: [row pair][sample]
   const int r = blockIdx.x / ngroups;
-  const int c0 = (blockIdx.x - r * ngroups) * GC;
-  const int nc = min(GC, C - c0);
+  const int cbeg = (blockIdx.x - r * ngroups) * (GC * gpc);
+  const int cend = min(C, cbeg + GC * gpc);
   const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
   if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) return;
-  const float* g_tile = gout + ((size_t)r * C + c0) * PER;
-  float* img = gt + (size_t)g.batch * H * W * C + c0;
   if (g.gw > kMaxG || g.gh > kMaxG) {  // reference-style scatter into the channels-last map
-    for (int e = threadIdx.x; e < nc * PER; e += NT) {
+    const float* g_tile = gout + ((size_t)r * C + cbeg) * PER;
+    float* img = gt + (size_t)g.batch * H * W * C + cbeg;
+    for (int e = threadIdx.x; e < (cend - cbeg) * PER; e += NT) {
       const int c = e / PER, b = e - c * PER;
       const int ph = b / P, pw = b - ph * P;
       const float go = g_tile[e] * g.inv_count;
@@ -537,14 +542,6 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
     }
     return;
   }
-  // stage the contiguous grad tile (read once, streaming)
-  if (((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_tile) & 15) == 0)) {
-    const float4* s4 = reinterpret_cast<const float4*>(g_tile);
-    float4* d4 = reinterpret_cast<float4*>(G_s);
-    for (int e = threadIdx.x; e < nc * PER / 4; e += NT) d4[e] = __ldcs(s4 + e);
-  } else {
-    for (int e = threadIdx.x; e < nc * PER; e += NT) G_s[e] = __ldcs(g_tile + e);
-  }
   build_tables<P, NT>(xtab, nullptr, g, H, W);
   for (int t = threadIdx.x; t < NW * g.gh; t += NT) {  // merged row slots of every (row pair, sample)
     const int j = t / g.gh, i = t - j * g.gh;
@@ -552,15 +549,32 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
         make_slots(make_tap_entry(g.sh, g.bh, 2 * j, i, g.gh, H, 1.f),
                    2 * j + 1 < P ? make_tap_entry(g.sh, g.bh, 2 * j + 1, i, g.gh, H, 1.f) : null_tap(), W * C);
   }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nch = lane < nc ? min(CPL, (nc - lane + 31) / 32) : 0;
-  if (nch == 0) return;
-  float* base = img + lane;
-  const float* grow = G_s + lane * PER + (2 * warp) * P;
   const bool row_b_exists = 2 * warp + 1 < P;
-  if (g.gh == 1) bwd_rows<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
-  else bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
+  for (int c0 = cbeg; c0 < cend; c0 += GC) {
+    const int nc = min(GC, cend - c0);
+    const float* g_tile = gout + ((size_t)r * C + c0) * PER;
+    float* img = gt + (size_t)g.batch * H * W * C + c0;
+    // stage the contiguous grad tile (read once, streaming)
+    if (((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_tile) & 15) == 0)) {
+      const float4* s4 = reinterpret_cast<const float4*>(g_tile);
+      float4* d4 = reinterpret_cast<float4*>(G_s);
+      for (int e = threadIdx.x; e < nc * PER / 4; e += NT) d4[e] = __ldcs(s4 + e);
+    } else {
+      for (int e = threadIdx.x; e < nc * PER; e += NT) G_s[e] = __ldcs(g_tile + e);
+    }
+    __syncthreads();  // tile (and, the first time round, the tables) visible
+    const int nch = lane < nc ? min(CPL, (nc - lane + 31) / 32) : 0;
+    if (nch > 0) {
+      float* base = img + lane;
+      const float* grow = G_s + lane * PER + (2 * warp) * P;
+      if (g.gh == 1)
+        bwd_rows<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
+      else
+        bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
+    }
+    if (c0 + GC < cend) __syncthreads();  // next group overwrites the tile
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -573,20 +587,22 @@ bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW) {
 
 size_t roi_cl_workspace_bytes(int N, int C, int H, int W) { return align_up((size_t)N * C * H * W * 4, 256); }
 
-int g_fwd_cpl = 2, g_bwd_cpl = 2;  // channels per lane (tuning knobs "roi_fwd_cpl" / "roi_bwd_cpl")
+int g_fwd_cpl = 2, g_bwd_cpl = 2;
+int g_roi_gpc = 2;  // 64-channel groups per CTA (tuning knob "roi_gpc")  // channels per lane (tuning knobs "roi_fwd_cpl" / "roi_bwd_cpl")
 
 template <int P, int CPL>
 static int launch_fwd_cl(const float* ft, const float* in, const float* rois, float* out, int N, int C, int H, int W,
                          int R, float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
   constexpr int PE = (P + 1) & ~1, NW = (P + 1) / 2;
-  const int ngroups = ceil_div(C, 32 * CPL);
+  const int gpc = max(1, g_roi_gpc);
+  const int ngroups = ceil_div(C, 32 * CPL * gpc);
   if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
   const int smem = 32 * CPL * P * P * 4 + 2 * PE * kMaxG * (int)sizeof(TapE);
   auto k = roi_align_fwd_cl_kernel<P, CPL>;
   cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ea != cudaSuccess) return (int)ea;
   k<<<(unsigned)((long long)R * ngroups), NW * 32, smem, stream>>>(ft, in, rois, out, N, C, H, W, R, scale,
-                                                                   sampling_ratio, aligned, ngroups);
+                                                                   sampling_ratio, aligned, ngroups, gpc);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -595,14 +611,15 @@ template <int P, int CPL>
 static int launch_bwd_cl(const float* gout, const float* rois, float* gt, int N, int C, int H, int W, int R,
                          float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
   constexpr int PE = (P + 1) & ~1, NW = (P + 1) / 2;
-  const int ngroups = ceil_div(C, 32 * CPL);
+  const int gpc = max(1, g_roi_gpc);
+  const int ngroups = ceil_div(C, 32 * CPL * gpc);
   if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
   const int smem = ((32 * CPL * P * P + 3) & ~3) * 4 + PE * kMaxG * (int)sizeof(TapE) + NW * kMaxG * (int)sizeof(YSlots);
   auto k = roi_align_bwd_cl_kernel<P, CPL>;
   cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ea != cudaSuccess) return (int)ea;
   k<<<(unsigned)((long long)R * ngroups), NW * 32, smem, stream>>>(gout, rois, gt, N, C, H, W, R, scale,
-                                                                   sampling_ratio, aligned, ngroups);
+                                                                   sampling_ratio, aligned, ngroups, gpc);
   count_launch();
   return (int)cudaGetLastError();
 }
