@@ -11,8 +11,9 @@
 // One kernel, C[M x N] = A[M x K] . B[N x K]^T, both operands K-major fp32:
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d of a [128 x 32] A tile and a [128 x 32] B tile per stage,
 //               128-byte swizzle, completion on an mbarrier
-//   warps 2-9   split: every thread rewrites its row of the freshly landed tiles in place (hi) and writes lo to a
-//               second tile with the same swizzled addresses; in GEMM 1 they also accumulate |x|^2 per row
+//   warps 2-9   split: every thread reads its row of the freshly landed tiles (= the hi operands as the tensor core
+//               sees them) and writes lo = x - trunc(x) to a second tile with the same swizzled addresses; in GEMM 1
+//               they also accumulate |x|^2 per row
 //   warp 1      allocates TMEM, issues 3 x 4 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) per stage from
 //               shared-memory descriptors, tcgen05.commit releases the stage / publishes the accumulator
 //   warps 10-13 epilogue: tcgen05.ld 32x32b, row scaling, global stores
@@ -195,17 +196,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int kb = 0; kb < num_kb; ++kb, ++g) {
         const int s = g % TC_STAGES;
         const uint32_t ph = (g / TC_STAGES) & 1;
-        mbar_wait(&conv_bar[s], ph);
+        // The tensor core reads fp32 words as TF32 by ignoring the low 13 mantissa bits, i.e. the freshly landed
+        // tiles ARE the hi operands: hi.hi can be issued as soon as the TMA data is there, while the split warps
+        // are still producing the lo tiles for the two cross terms.
+        mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_TILE_BYTES);
+        const uint64_t b_hi = make_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = make_desc_sw128(st + 3 * TC_TILE_BYTES);
         if (lane == 0) {
-          const uint32_t st = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
-          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_TILE_BYTES);
-          const uint64_t b_hi = make_desc_sw128(st + 2 * TC_TILE_BYTES),
-                         b_lo = make_desc_sw128(st + 3 * TC_TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 B per K=8 step inside the swizzle row
             umma_tf32(acc, a_hi + adv, b_hi + adv, kIdescTf32, (kb | k) != 0);
+          }
+        }
+        __syncwarp();
+        mbar_wait(&conv_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
             umma_tf32(acc, a_hi + adv, b_lo + adv, kIdescTf32, 1u);
             umma_tf32(acc, a_lo + adv, b_hi + adv, kIdescTf32, 1u);
           }
@@ -239,16 +251,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const int cc = c ^ (t & 7);
           if (op == 0)
             ss = fmaf(v[c].x, v[c].x, fmaf(v[c].y, v[c].y, fmaf(v[c].z, v[c].z, fmaf(v[c].w, v[c].w, ss))));
-          float4 h, l;
-          h.x = to_tf32(v[c].x);
-          h.y = to_tf32(v[c].y);
-          h.z = to_tf32(v[c].z);
-          h.w = to_tf32(v[c].w);
-          l.x = v[c].x - h.x;  // exact; the tensor core drops its low bits (2^-21 |v|)
-          l.y = v[c].y - h.y;
-          l.z = v[c].z - h.z;
-          l.w = v[c].w - h.w;
-          hi[cc] = h;
+          float4 l;  // lo = v - trunc_tf32(v): exact in fp32; the tensor core drops its low bits (2^-21 |v|)
+          l.x = v[c].x - to_tf32(v[c].x);
+          l.y = v[c].y - to_tf32(v[c].y);
+          l.z = v[c].z - to_tf32(v[c].z);
+          l.w = v[c].w - to_tf32(v[c].w);
           lo[cc] = l;
         }
         // |x|^2 of the tile's rows travels with the last stage: written before the arrive the MMA (and through its
