@@ -7,10 +7,11 @@
 //   1. (coordinate-trick mode only) max over all coordinates               -> nms_max_kernel
 //   2. stable descending radix sort of (score, index)                      -> cub::DeviceRadixSort
 //   3. gather boxes (+ class offset) / class ids into sorted order          -> nms_gather_kernel
-//   4. 64x64-tile IoU bitmask, upper triangle only, warp-ballot rows        -> nms_mask_kernel
-//   5. greedy scan on the device: per 64-box block resolve the diagonal tile serially in registers,
-//      then OR the kept rows into the removed-bitmap in parallel; kept indices are emitted in order
-//                                                                          -> nms_scan_kernel
+//   4. 64x64-tile IoU bitmask, upper triangle only; diagonal tiles also emit the column view of the
+//      suppression relation with warp ballots                              -> nms_mask_kernel
+//   5. greedy scan on the device: per 64-box block a warp-ballot fix-point resolves the diagonal tile, the
+//      kept rows (mask words prefetched one block ahead) are OR-ed into the removed-bitmap, kept indices are
+//      emitted in order                                                    -> nms_scan_kernel
 // IoU arithmetic is fp32 without FMA contraction ((area_i + area_j) - inter, IEEE division) and the
 // threshold test promotes the fp32 IoU to double, exactly like the CPU kernel (oracle/c/nms_ref.c).
 #include <cub/device/device_radix_sort.cuh>
@@ -82,14 +83,18 @@ __device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float a
 }
 
 // grid (col_blocks, row_blocks), 64 threads; only tiles with col_block >= row_block are computed.
+// Row masks: mask[i][cb] bit j = box (cb*64+j) is suppressed by box i (j > i inside a diagonal tile).
+// Diagonal tiles additionally emit the COLUMN view through warp ballots: coldiag[rb*64+j] bit i = row i (< j, same
+// tile) suppresses j — what the scan kernel's ballot fix-point needs.
 __global__ void __launch_bounds__(kTile)
 nms_mask_kernel(const float4* __restrict__ sboxes, const int* __restrict__ scls, int M, double thr, int col_blocks,
-                unsigned long long* __restrict__ mask) {
+                unsigned long long* __restrict__ mask, unsigned long long* __restrict__ coldiag) {
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;
   __shared__ float4 cbox[kTile];
   __shared__ float carea[kTile];
   __shared__ int ccls[kTile];
+  __shared__ unsigned int colpart[2][kTile];
   const int ncol = min(M - cb * kTile, kTile);
   if (threadIdx.x < ncol) {
     const float4 b = sboxes[cb * kTile + threadIdx.x];
@@ -99,57 +104,85 @@ nms_mask_kernel(const float4* __restrict__ sboxes, const int* __restrict__ scls,
   }
   __syncthreads();
   const int i = rb * kTile + threadIdx.x;
-  if (i >= M) return;
-  const float4 a = sboxes[i];
+  const bool row_ok = i < M;
+  const float4 a = row_ok ? sboxes[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-  const int cls_a = scls[i];
+  const int cls_a = row_ok ? scls[i] : -1;
   unsigned long long bits = 0ull;
-  const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-  for (int j = start; j < ncol; ++j) {
-    if (ccls[j] == cls_a && iou_over(a, cbox[j], area_a, carea[j], thr)) bits |= 1ull << j;
+  if (rb != cb) {
+    if (!row_ok) return;
+    for (int j = 0; j < ncol; ++j)
+      if (ccls[j] == cls_a && iou_over(a, cbox[j], area_a, carea[j], thr)) bits |= 1ull << j;
+    mask[(size_t)i * col_blocks + cb] = bits;
+    return;
   }
-  mask[(size_t)i * col_blocks + cb] = bits;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = 0; j < kTile; ++j) {  // uniform trip count: every lane takes part in every ballot
+    const bool p = row_ok && j < ncol && j > (int)threadIdx.x && ccls[j] == cls_a &&
+                   iou_over(a, cbox[j], area_a, carea[j], thr);
+    if (p) bits |= 1ull << j;
+    const unsigned int m = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) colpart[warp][j] = m;
+  }
+  if (row_ok) mask[(size_t)i * col_blocks + cb] = bits;
+  __syncthreads();
+  coldiag[(size_t)rb * kTile + threadIdx.x] =
+      (unsigned long long)colpart[0][threadIdx.x] | ((unsigned long long)colpart[1][threadIdx.x] << 32);
 }
 
-// One CTA.  remv[] (shared) = bitmap of suppressed boxes.  For block b: thread 0..63 fetch the diagonal
-// words, thread 0 resolves the block serially (<= 64 dependent bit-ops), then ALL 1024 threads OR the rows of
-// the kept boxes into the removed-bitmap: thread (slot, word) takes every 4th kept row of one column word and
-// issues its loads in batches of four independent requests (the first version issued one dependent L2 load
-// per kept row and spent 18 us per block).
+// One CTA, 1024 threads.  remv[] (shared) = bitmap of suppressed boxes.  Per 64-box block b:
+//   * warp 0 resolves the block with a ballot fix-point on the column masks: kept_{n+1} = alive & ~{ j : some kept_n
+//     row i < j suppresses j } — its unique fixed point is the greedy result, reached in (longest suppression chain
+//     + 1) rounds of two ballots instead of up to 64 dependent steps;
+//   * every thread owns (16 rows, 1 column word) of the block's rows and has ALREADY loaded those 16 mask words one
+//     block ahead (the loads do not depend on the scan state), so applying the kept rows to the removed-bitmap is
+//     register work; column words beyond the first 256 are fetched in batches of 16 independent loads.
 __global__ void __launch_bounds__(1024)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int M, int col_blocks,
-                int64_t* __restrict__ keep, int32_t* __restrict__ num_keep) {
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long long* __restrict__ coldiag,
+                const int* __restrict__ order, int M, int col_blocks, int64_t* __restrict__ keep,
+                int32_t* __restrict__ num_keep) {
   extern __shared__ unsigned long long remv[];  // [col_blocks]
-  __shared__ unsigned long long diag[kTile];
   __shared__ unsigned long long kept_s;
   __shared__ int count_s;
   for (int w = threadIdx.x; w < col_blocks; w += blockDim.x) remv[w] = 0ull;
   if (threadIdx.x == 0) count_s = 0;
-  __syncthreads();
-  const int slot = threadIdx.x >> 8;        // 0..3: which quarter of the kept rows
-  const int wlane = threadIdx.x & 255;      // column word within a pass of 256
+  const int slot = threadIdx.x >> 8;    // 0..3: rows t with t % 4 == slot
+  const int wlane = threadIdx.x & 255;  // column word within a pass of 256
+  const int lane = threadIdx.x & 31;
   unsigned int* remv32 = reinterpret_cast<unsigned int*>(remv);
-  // diagonal words do not depend on the scan state: fetch block b+1's while block b is being resolved
-  unsigned long long dnext = 0ull;
-  if (threadIdx.x < kTile && threadIdx.x < M) dnext = mask[(size_t)threadIdx.x * col_blocks];
+
+  // v[u] = mask word (row b*64 + 4u + slot, column word w), 0 outside the matrix
+#define NMS_LOAD_ROWS(B, WORD, V)                                                             \
+  _Pragma("unroll") for (int u = 0; u < 16; ++u) {                                            \
+    const int row_ = (B) * kTile + 4 * u + slot;                                              \
+    (V)[u] = ((WORD) < col_blocks && row_ < M) ? mask[(size_t)row_ * col_blocks + (WORD)] : 0ull; \
+  }
+  unsigned long long v[16];  // prefetched for the block about to be resolved
+  NMS_LOAD_ROWS(0, 1 + wlane, v)
+  unsigned long long cm_lo = 0ull, cm_hi = 0ull;  // column masks of block 0 for warp 0
+  if (threadIdx.x < 32) {
+    cm_lo = coldiag[lane];
+    cm_hi = coldiag[lane + 32];
+  }
+  __syncthreads();
   for (int b = 0; b < col_blocks; ++b) {
     const int nb = min(M - b * kTile, kTile);
-    if (threadIdx.x < kTile) {
-      diag[threadIdx.x] = threadIdx.x < nb ? dnext : 0ull;
-      const int nr = (b + 1) * kTile + threadIdx.x;
-      dnext = (b + 1 < col_blocks && nr < M) ? mask[(size_t)nr * col_blocks + b + 1] : 0ull;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
       unsigned long long alive = ~remv[b];
       if (nb < kTile) alive &= (1ull << nb) - 1ull;
-      unsigned long long kept = 0ull;
-      while (alive) {
-        const int t = __ffsll((long long)alive) - 1;
-        kept |= 1ull << t;
-        alive &= ~(diag[t] | (1ull << t));
+      unsigned long long kept = alive;
+      for (int it = 0; it < kTile + 1; ++it) {
+        const unsigned int s_lo = __ballot_sync(0xffffffffu, (cm_lo & kept) != 0ull);
+        const unsigned int s_hi = __ballot_sync(0xffffffffu, (cm_hi & kept) != 0ull);
+        const unsigned long long nk = alive & ~((unsigned long long)s_lo | ((unsigned long long)s_hi << 32));
+        if (nk == kept) break;
+        kept = nk;
       }
-      kept_s = kept;
+      if (lane == 0) kept_s = kept;
+      if (b + 1 < col_blocks) {  // next block's column masks, consumed one iteration later
+        cm_lo = coldiag[(size_t)(b + 1) * kTile + lane];
+        cm_hi = coldiag[(size_t)(b + 1) * kTile + lane + 32];
+      }
     }
     __syncthreads();
     const unsigned long long kept = kept_s;
@@ -158,31 +191,35 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       const int pos = base + __popcll(kept & ((1ull << threadIdx.x) - 1ull));
       keep[pos] = (int64_t)order[b * kTile + threadIdx.x];
     }
-    // this thread's share of the kept rows: rows t with t % 4 == slot
-    const unsigned long long mine = kept & (0x1111111111111111ull << slot);
-    for (int w = b + 1 + wlane; w < col_blocks; w += 256) {
-      const unsigned long long* col = mask + (size_t)b * kTile * col_blocks + w;
-      unsigned long long acc = 0ull, k = mine;
-      while (k) {
-        unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
+    {  // first pass of column words: the prefetched registers
+      const int w = b + 1 + wlane;
+      unsigned long long acc = 0ull;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (k) {
-            const int t = __ffsll((long long)k) - 1;
-            k &= k - 1ull;
-            v[u] = col[(size_t)t * col_blocks];
-          }
-        }
-        acc |= (v[0] | v[1]) | (v[2] | v[3]);
+      for (int u = 0; u < 16; ++u)
+        if ((kept >> (4 * u + slot)) & 1ull) acc |= v[u];
+      if (acc && w < col_blocks) {
+        atomicOr(remv32 + 2 * w, (unsigned int)acc);
+        atomicOr(remv32 + 2 * w + 1, (unsigned int)(acc >> 32));
       }
+    }
+    for (int w = b + 1 + wlane + 256; w < col_blocks; w += 256) {  // wider problems: 16 independent loads per pass
+      NMS_LOAD_ROWS(b, w, v)
+      unsigned long long acc = 0ull;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if ((kept >> (4 * u + slot)) & 1ull) acc |= v[u];
       if (acc) {
         atomicOr(remv32 + 2 * w, (unsigned int)acc);
         atomicOr(remv32 + 2 * w + 1, (unsigned int)(acc >> 32));
       }
     }
+    // the next block's rows do not depend on the scan state: fetch them now, use them after the next resolve
+    if (b + 1 < col_blocks) {
+      NMS_LOAD_ROWS(b + 1, b + 2 + wlane, v)
+    }
     __syncthreads();
     if (threadIdx.x == 0) count_s = base + __popcll(kept);
-    // (count_s is re-read after the next iteration's barriers)
+    // (count_s and kept_s are next touched after the barrier above / the next iteration's barrier)
   }
   __syncthreads();
   if (threadIdx.x == 0) *num_keep = count_s;
@@ -197,6 +234,7 @@ struct NmsWs {
   int* scls;
   float* max_coord;
   unsigned long long* mask;
+  unsigned long long* coldiag;
   void* cub_temp;
   size_t cub_bytes;
   size_t total;
@@ -220,6 +258,7 @@ static NmsWs carve(void* base, int64_t M) {
   w.scls = (int*)take(m * 4);
   w.max_coord = (float*)take(4);
   w.mask = (unsigned long long*)take(m * cb * 8);
+  w.coldiag = (unsigned long long*)take(cb * kTile * 8);
   w.cub_bytes = 0;
   cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float*)nullptr, (float*)nullptr,
                                             (const int*)nullptr, (int*)nullptr, (int)m, 0, 32, (cudaStream_t)0);
@@ -266,12 +305,12 @@ extern "C" int cddmsl_nms(const float* boxes, const float* scores, const int64_t
                                                            w.max_coord, coord_trick, w.sboxes, w.scls, m);
   count_launch();
   nms_mask_kernel<<<dim3(col_blocks, col_blocks), kTile, 0, stream>>>(w.sboxes, w.scls, m, iou_threshold,
-                                                                      col_blocks, w.mask);
+                                                                      col_blocks, w.mask, w.coldiag);
   count_launch();
   const int smem = col_blocks * 8;
   if (smem > 48 * 1024)
     CDDMSL_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  nms_scan_kernel<<<1, 1024, smem, stream>>>(w.mask, w.order, m, col_blocks, keep, num_keep);
+  nms_scan_kernel<<<1, 1024, smem, stream>>>(w.mask, w.coldiag, w.order, m, col_blocks, keep, num_keep);
   count_launch();
   CDDMSL_CHECK_LAUNCH();
   return CDDMSL_OK;
