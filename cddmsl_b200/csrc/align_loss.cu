@@ -34,56 +34,135 @@ __device__ __forceinline__ const float* packed_row(const float* packed_all, int 
   return packed_all + ((size_t)(rk * 2 + which) * n_local + li) * D;
 }
 
-// S[i][j] = A^_i . B^_j ; 32x32 tile per CTA, 256 threads (2x2 micro-tile), K-chunks of 32
+// S[i][j] = A^_i . B^_j ; 64x64 tile per CTA, 256 threads (4x4 micro-tile), K-chunks of 16 staged k-major so
+// the inner product reads its four rows / four columns with one LDS.128 each.
+constexpr int kLT = 64, kLK = 16;
 __global__ void __launch_bounds__(256)
 align_logits_kernel(const float* __restrict__ packed_all, int n, int n_local, int D, float* __restrict__ S) {
-  __shared__ float As[32][33], Bs[32][33];
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  __shared__ __align__(16) float As[kLK][kLT + 4], Bs[kLK][kLT + 4];
+  const int i0 = blockIdx.y * kLT, j0 = blockIdx.x * kLT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < D; k0 += 32) {
-    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
-      const int rr = e >> 5, kk = e & 31;
-      const int k = k0 + kk;
-      As[rr][kk] = (i0 + rr < n && k < D) ? packed_row(packed_all, n_local, D, 0, i0 + rr)[k] : 0.f;
-      Bs[rr][kk] = (j0 + rr < n && k < D) ? packed_row(packed_all, n_local, D, 1, j0 + rr)[k] : 0.f;
+  const int lrow = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;  // loader: one row, four consecutive k
+  const float* arow = i0 + lrow < n ? packed_row(packed_all, n_local, D, 0, i0 + lrow) : nullptr;
+  const float* brow = j0 + lrow < n ? packed_row(packed_all, n_local, D, 1, j0 + lrow) : nullptr;
+  const bool vec = (D & 3) == 0;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float av[4], bv[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) av[c] = bv[c] = 0.f;
+    const int k = k0 + lk;
+    if (vec) {
+      if (k < D) {
+        if (arow) {
+          const float4 t = *reinterpret_cast<const float4*>(arow + k);
+          av[0] = t.x, av[1] = t.y, av[2] = t.z, av[3] = t.w;
+        }
+        if (brow) {
+          const float4 t = *reinterpret_cast<const float4*>(brow + k);
+          bv[0] = t.x, bv[1] = t.y, bv[2] = t.z, bv[3] = t.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (arow && k + c < D) av[c] = arow[k + c];
+        if (brow && k + c < D) bv[c] = brow[k + c];
+      }
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < D; k0 += kLK) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      As[lk + c][lrow] = av[c];
+      Bs[lk + c][lrow] = bv[c];
     }
     __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < 32; ++kk) {
-      const float a0 = As[ty][kk], a1 = As[ty + 16][kk];
-      const float b0 = Bs[tx][kk], b1 = Bs[tx + 16][kk];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]);
-      acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]);
-      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    if (k0 + kLK < D) fetch(k0 + kLK);  // next chunk's global loads fly under this chunk's FMAs
+#pragma unroll
+    for (int kk = 0; kk < kLK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int x = 0; x < 4; ++x) {
+    const int i = i0 + ty * 4 + x, j = j0 + tx * 4;
+    if (i >= n) continue;
+    if ((n & 3) == 0 && j + 3 < n) {
+      *reinterpret_cast<float4*>(S + (size_t)i * n + j) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+    } else {
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-      if (i < n && j < n) S[(size_t)i * n + j] = acc[a][b];
+      for (int y = 0; y < 4; ++y)
+        if (j + y < n) S[(size_t)i * n + j + y] = acc[x][y];
     }
+  }
 }
 
-// warp w < n: row log-sum-exp of S;  warp n + w: column log-sum-exp
-__global__ void align_lse_kernel(const float* __restrict__ S, int n, float* __restrict__ rowlse,
-                                 float* __restrict__ collse) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= 2 * n) return;
-  const bool col = w >= n;
-  const int i = col ? w - n : w;
-  const size_t stride = col ? (size_t)n : 1, base = col ? (size_t)i : (size_t)i * n;
-  float m = -INFINITY;
-  for (int j = lane; j < n; j += 32) m = fmaxf(m, S[base + j * stride]);
-  m = warp_max(m);
-  float se = 0.f;
-  for (int j = lane; j < n; j += 32) se += expf(S[base + j * stride] - m);
-  se = warp_sum(se);
-  if (lane == 0) (col ? collse : rowlse)[i] = logf(se) + m;
+// blocks [0, row_blocks): one warp per row of S (coalesced along the row);
+// blocks [row_blocks, ..): one CTA per 32 columns -- lane = column, the 32 warps stride over the rows (eight loads in
+// flight each) with an online (max, sum-exp) pair and merge through shared memory: the column pass is coalesced too.
+constexpr int kLseWarps = 32;
+__global__ void __launch_bounds__(kLseWarps * 32)
+align_lse_kernel(const float* __restrict__ S, int n, int row_blocks, float* __restrict__ rowlse,
+                 float* __restrict__ collse) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x < row_blocks) {
+    const int i = blockIdx.x * kLseWarps + warp;
+    if (i >= n) return;
+    const float* row = S + (size_t)i * n;
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float se = 0.f;
+    for (int j = lane; j < n; j += 32) se += expf(row[j] - m);
+    se = warp_sum(se);
+    if (lane == 0) rowlse[i] = logf(se) + m;
+    return;
+  }
+  __shared__ float sm[kLseWarps][32], ss[kLseWarps][32];
+  const int j = (blockIdx.x - row_blocks) * 32 + lane;
+  float m = -INFINITY, se = 0.f;
+  if (j < n) {
+    for (int i = warp; i < n; i += kLseWarps * 8) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int ii = i + u * kLseWarps;
+        x[u] = ii < n ? S[(size_t)ii * n + j] : -INFINITY;
+      }
+      float cm = x[0];
+#pragma unroll
+      for (int u = 1; u < 8; ++u) cm = fmaxf(cm, x[u]);
+      if (cm > m) {
+        se *= expf(m - cm);  // expf(-inf) == 0 covers the first batch
+        m = cm;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) se += expf(x[u] - m);
+    }
+  }
+  sm[warp][lane] = m;
+  ss[warp][lane] = se;
+  __syncthreads();
+  if (warp == 0 && j < n) {
+    float mm = sm[0][lane];
+    for (int w = 1; w < kLseWarps; ++w) mm = fmaxf(mm, sm[w][lane]);
+    float tot = 0.f;
+    for (int w = 0; w < kLseWarps; ++w) tot += ss[w][lane] == 0.f ? 0.f : ss[w][lane] * expf(sm[w][lane] - mm);
+    collse[j] = logf(tot) + mm;
+  }
 }
 
 __global__ void align_loss_kernel(const float* __restrict__ S, int n, const float* __restrict__ rowlse,
@@ -104,49 +183,136 @@ __global__ void align_loss_kernel(const float* __restrict__ S, int n, const floa
   }
 }
 
-// CTA b < n_local: gradient of local A row;  b >= n_local: local B row.
+// Gradient of this rank's rows.  CTA (x, y): x < gb owns kGR consecutive local src rows, x >= gb tgt rows; y picks a
+// 64-column slab of D.  Every row of the other side streamed from L2 feeds kGR accumulators; the 256 threads are
+// 64 columns x 4 interleaved j-partitions (eight loads in flight per thread), merged through shared memory.
 //   dS_ij = (softmax_row(S)_ij + softmax_col(S)_ij - 2 [i==j]) / (2n)
-//   dA^_i = sum_j dS_ij B^_j ,  dB^_j = sum_i dS_ij A^_i ,  d(x) = (dx^ - x^ (x^ . dx^)) / |x|
+//   dA^_i = sum_j dS_ij B^_j ,  dB^_j = sum_i dS_ij A^_i
+// The coefficients of a chunk of kGJ opposite rows are staged in shared memory as coef[j][r] (two LDS.128 per j).
+// Writes the raw dx^; align_grad_finish_kernel applies d(x) = (dx^ - x^ (x^ . dx^)) / |x|.
+constexpr int kGR = 8, kGJ = 1024, kGD = 64, kGP = 4;
 __global__ void __launch_bounds__(256)
-align_grad_kernel(const float* __restrict__ packed_all, const float* __restrict__ norms_local,
-                  const float* __restrict__ S, const float* __restrict__ rowlse, const float* __restrict__ collse,
-                  int n, int n_local, int D, int row0, const float* __restrict__ grad_scale, float* __restrict__ da,
-                  float* __restrict__ db) {
-  extern __shared__ float coef[];  // [n]
-  __shared__ float red[8];
-  const bool bside = (int)blockIdx.x >= n_local;
-  const int li = bside ? blockIdx.x - n_local : blockIdx.x;
+align_grad_kernel(const float* __restrict__ packed_all, const float* __restrict__ S,
+                  const float* __restrict__ rowlse, const float* __restrict__ collse, int n, int n_local, int D,
+                  int row0, const float* __restrict__ grad_scale, float* __restrict__ da, float* __restrict__ db) {
+  __shared__ __align__(16) float coef[kGJ][kGR];
+  __shared__ unsigned rowoff[kGJ];  // float offset of opposite row j inside packed_all (no division in the hot loop)
+  const int gb = gridDim.x >> 1;
+  const bool bside = (int)blockIdx.x >= gb;
+  const int l0 = (bside ? blockIdx.x - gb : blockIdx.x) * kGR;
   float* out = bside ? db : da;
   if (!out) return;
-  const int gi = row0 + li;
+  const int rows = min(kGR, n_local - l0);
+  const int g0 = row0 + l0;
   const float scale = (grad_scale ? *grad_scale : 1.f) * 0.5f / (float)n;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    // a-side walks row gi of S, b-side walks column gi
-    const float s = bside ? S[(size_t)j * n + gi] : S[(size_t)gi * n + j];
-    const float pr = expf(s - (bside ? rowlse[j] : rowlse[gi]));
-    const float pc = expf(s - (bside ? collse[gi] : collse[j]));
-    coef[j] = scale * (pr + pc - (j == gi ? 2.f : 0.f));
+  const int tid = threadIdx.x, dl = tid & (kGD - 1), jp = tid / kGD;
+  const int d = blockIdx.y * kGD + dl;
+  const bool dok = d < D;
+  const int other = bside ? 0 : 1;
+
+  float acc[kGR];
+#pragma unroll
+  for (int r = 0; r < kGR; ++r) acc[r] = 0.f;
+  for (int jc = 0; jc < n; jc += kGJ) {
+    const int jn = min(kGJ, n - jc);
+    __syncthreads();
+    if (bside) {
+      // column block S[j][g0 .. g0+7]: eight lanes share one 32-byte sector
+      const int r = tid & 7;
+      const float cl = r < rows ? collse[g0 + r] : 0.f;
+      for (int jb = tid >> 3; jb < jn; jb += 32 * 4) {
+        float sv[4], rl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = jc + min(jb + u * 32, jn - 1);
+          sv[u] = r < rows ? S[(size_t)j * n + g0 + r] : 0.f;
+          rl[u] = rowlse[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = jb + u * 32, j = jc + jj;
+          if (jj < jn)
+            coef[jj][r] = r < rows ? scale * (expf(sv[u] - rl[u]) + expf(sv[u] - cl) - (j == g0 + r ? 2.f : 0.f)) : 0.f;
+        }
+      }
+    } else {
+      for (int jj = tid; jj < jn; jj += 256) {
+        const int j = jc + jj;
+        const float cl = collse[j];
+#pragma unroll
+        for (int r = 0; r < kGR; ++r) {
+          float c = 0.f;
+          if (r < rows) {
+            const float s = S[(size_t)(g0 + r) * n + j];
+            c = scale * (expf(s - rowlse[g0 + r]) + expf(s - cl) - (j == g0 + r ? 2.f : 0.f));
+          }
+          coef[jj][r] = c;
+        }
+      }
+    }
+    for (int jj = tid; jj < jn; jj += 256)
+      rowoff[jj] = (unsigned)(packed_row(packed_all, n_local, D, other, jc + jj) - packed_all);
+    __syncthreads();
+    if (dok) {
+      const float* col = packed_all + d;
+      for (int jj = jp; jj < jn; jj += kGP * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(col + rowoff[min(jj + u * kGP, jn - 1)]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j2 = jj + u * kGP;
+          const float x = j2 < jn ? v[u] : 0.f;
+          const int jq = min(j2, jn - 1);
+          const float4 c0 = *reinterpret_cast<const float4*>(&coef[jq][0]);
+          const float4 c1 = *reinterpret_cast<const float4*>(&coef[jq][4]);
+          acc[0] = fmaf(c0.x, x, acc[0]);
+          acc[1] = fmaf(c0.y, x, acc[1]);
+          acc[2] = fmaf(c0.z, x, acc[2]);
+          acc[3] = fmaf(c0.w, x, acc[3]);
+          acc[4] = fmaf(c1.x, x, acc[4]);
+          acc[5] = fmaf(c1.y, x, acc[5]);
+          acc[6] = fmaf(c1.z, x, acc[6]);
+          acc[7] = fmaf(c1.w, x, acc[7]);
+        }
+      }
+    }
   }
+  // merge the four j-partitions (coef is free again after the barrier)
   __syncthreads();
-  const float* self = packed_row(packed_all, n_local, D, bside ? 1 : 0, gi);
-  const float nrm = norms_local[(bside ? n_local : 0) + li];
-  // D is processed in slabs of blockDim.x columns; the projection needs the full dot first
-  float dot_part = 0.f;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float acc = 0.f;
-    for (int j = 0; j < n; ++j) acc = fmaf(coef[j], packed_row(packed_all, n_local, D, bside ? 0 : 1, j)[d], acc);
-    out[(size_t)li * D + d] = acc;  // raw dx^ parked in the output, fixed up below
-    dot_part = fmaf(acc, self[d], dot_part);
+  float* red = &coef[0][0];  // [kGP][kGR][kGD]
+#pragma unroll
+  for (int r = 0; r < kGR; ++r) red[(jp * kGR + r) * kGD + dl] = acc[r];
+  __syncthreads();
+  for (int e = tid; e < kGR * kGD; e += 256) {
+    const int r = e / kGD, c = e % kGD;
+    const int dd = blockIdx.y * kGD + c;
+    if (r < rows && dd < D) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < kGP; ++q) t += red[(q * kGR + r) * kGD + c];
+      out[(size_t)(l0 + r) * D + dd] = t;
+    }
   }
-  dot_part = warp_sum(dot_part);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot_part;
-  __syncthreads();
+}
+
+// one warp per local row (rows [0,n_local): src, then tgt): projection through the normalisation, in place
+__global__ void align_grad_finish_kernel(const float* __restrict__ packed_all, const float* __restrict__ norms_local,
+                                         int n_local, int D, int row0, float* __restrict__ da,
+                                         float* __restrict__ db) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= 2 * n_local) return;
+  const bool bside = w >= n_local;
+  const int li = bside ? w - n_local : w;
+  float* out = bside ? db : da;
+  if (!out) return;
+  out += (size_t)li * D;
+  const float* self = packed_row(packed_all, n_local, D, bside ? 1 : 0, row0 + li);
   float dot = 0.f;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) dot += red[i];
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float g = out[(size_t)li * D + d];
-    out[(size_t)li * D + d] = (g - self[d] * dot) / nrm;
-  }
+  for (int d = lane; d < D; d += 32) dot = fmaf(out[d], self[d], dot);
+  dot = warp_sum(dot);
+  const float nrm = norms_local[w];
+  for (int d = lane; d < D; d += 32) out[d] = (out[d] - self[d] * dot) / nrm;
 }
 
 struct AlignWs {
@@ -208,18 +374,19 @@ extern "C" int cddmsl_align_loss(const float* packed_all, const float* norms_loc
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return CDDMSL_EALIGN;
   AlignWs w = align_carve(workspace, n);
   if (w.total > workspace_bytes) return CDDMSL_EWORKSPACE;
-  const int tiles = ceil_div(n, 32);
+  const int tiles = ceil_div(n, kLT);
+  const int row_blocks = ceil_div(n, kLseWarps);
   align_logits_kernel<<<dim3(tiles, tiles), 256, 0, stream>>>(packed_all, n, n_local, D, w.S);
-  align_lse_kernel<<<ceil_div(2 * n * 32, 256), 256, 0, stream>>>(w.S, n, w.rowlse, w.collse);
+  align_lse_kernel<<<row_blocks + ceil_div(n, 32), kLseWarps * 32, 0, stream>>>(w.S, n, row_blocks, w.rowlse,
+                                                                               w.collse);
   align_loss_kernel<<<1, 256, 0, stream>>>(w.S, n, w.rowlse, w.collse, loss);
   count_launch(3);
-  if (da || db) {
-    const int smem = n * 4;
-    if (smem > 48 * 1024)
-      CDDMSL_CUDA(cudaFuncSetAttribute(align_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    align_grad_kernel<<<2 * n_local, 256, smem, stream>>>(packed_all, norms_local, w.S, w.rowlse, w.collse, n,
-                                                          n_local, D, rank * n_local, grad_scale, da, db);
-    count_launch();
+  if ((da || db) && n_local > 0) {
+    align_grad_kernel<<<dim3(2 * ceil_div(n_local, kGR), ceil_div(D, kGD)), 256, 0, stream>>>(
+        packed_all, w.S, w.rowlse, w.collse, n, n_local, D, rank * n_local, grad_scale, da, db);
+    align_grad_finish_kernel<<<ceil_div(2 * n_local * 32, 256), 256, 0, stream>>>(packed_all, norms_local, n_local, D,
+                                                                                  rank * n_local, da, db);
+    count_launch(2);
   }
   CDDMSL_CHECK_LAUNCH();
   return CDDMSL_OK;

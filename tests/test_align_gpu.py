@@ -79,7 +79,8 @@ def test_two_rank_fixture_from_real_gatherlayer(golden_dir):
         _close(db.cpu().numpy(), w[f"db{r}"], 1e-4, f"db{r}")
 
 
-@pytest.mark.parametrize("world,n_local,dim", [(8, 256, 256), (4, 32, 256), (3, 5, 64)])
+@pytest.mark.parametrize("world,n_local,dim", [(8, 256, 256), (4, 32, 256), (3, 5, 64), (2, 16, 1024),
+                                               (2, 9, 1300), (1, 3, 30), (2, 600, 64)])
 def test_world_emulation_vs_oracle(world, n_local, dim):
     """configs[2]: 8 ranks x 16 regions x 16 images = 2048 gathered rows."""
     g = synth.generator(world * 100 + n_local)
