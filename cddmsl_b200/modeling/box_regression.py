@@ -13,9 +13,15 @@ class Box2BoxTransform:
         self.weights = weights
         self.scale_clamp = scale_clamp
 
-    def get_deltas(self, src_boxes: torch.Tensor, target_boxes: torch.Tensor) -> torch.Tensor:
+    def get_deltas(self, src_boxes: torch.Tensor, target_boxes: torch.Tensor,
+                   valid: "torch.Tensor | None" = None) -> torch.Tensor:
+        """`valid` (bool [N], optional): rows outside it are don't-care -- their widths are replaced by 1 and the
+        validity assert (a device->host sync) is skipped; used by the sync-free box-regression loss."""
         sw = src_boxes[:, 2] - src_boxes[:, 0]
         sh = src_boxes[:, 3] - src_boxes[:, 1]
+        if valid is not None:
+            sw = torch.where(valid & (sw > 0), sw, torch.ones_like(sw))
+            sh = torch.where(valid & (sh > 0), sh, torch.ones_like(sh))
         sx = src_boxes[:, 0] + 0.5 * sw
         sy = src_boxes[:, 1] + 0.5 * sh
         tw = target_boxes[:, 2] - target_boxes[:, 0]
@@ -25,7 +31,8 @@ class Box2BoxTransform:
         wx, wy, ww, wh = self.weights
         deltas = torch.stack((wx * (tx - sx) / sw, wy * (ty - sy) / sh, ww * torch.log(tw / sw),
                               wh * torch.log(th / sh)), dim=1)
-        assert (sw > 0).all().item(), "Input boxes to Box2BoxTransform are not valid!"
+        if valid is None:
+            assert (sw > 0).all().item(), "Input boxes to Box2BoxTransform are not valid!"
         return deltas
 
     def apply_deltas(self, deltas: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:

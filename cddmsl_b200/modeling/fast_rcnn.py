@@ -33,9 +33,14 @@ from ..structures import Boxes, Instances
 
 _storage_hook = None  # callable(name, value) — e.g. detectron2's get_event_storage().put_scalar
 
+# True: `box_reg_loss` selects the foreground rows with `nonzero` and asserts on degenerate boxes exactly like the
+# reference (two device->host syncs per step); False (default): the same sum evaluated with a mask, no sync.
+STRICT_BOX_REG_SYNC = False
+
 
 def set_scalar_sink(fn) -> None:
-    """Where `fast_rcnn/cls_accuracy` & co. go (the reference writes them to EventStorage, :123-127)."""
+    """Where `fast_rcnn/cls_accuracy` & co. go (the reference writes them to EventStorage, :123-127).
+    With no sink registered the statistics are not read back at all (no device->host sync in `losses`)."""
     global _storage_hook
     _storage_hook = fn
 
@@ -61,7 +66,7 @@ def _log_classification_stats(pred_logits, gt_classes, prefix="fast_rcnn", count
     """fast_rcnn.py:100-127.  `counters` = int32[4] from the fused kernel (accurate, fg, fg accurate,
     false negative); without it the reference arithmetic is evaluated in PyTorch."""
     num_instances = gt_classes.numel()
-    if num_instances == 0:
+    if num_instances == 0 or _storage_hook is None:
         return
     if counters is not None:
         num_accurate, num_fg, fg_num_accurate, num_false_negative = counters.tolist()
@@ -325,16 +330,34 @@ class FastRCNNOutputLayers(nn.Module):
     def box_reg_loss(self, proposal_boxes, gt_boxes, pred_deltas, gt_classes):
         """fast_rcnn.py:646-689 (smooth-L1 on foreground rows, normalised by R)."""
         box_dim = proposal_boxes.shape[1]
-        fg_inds = nonzero_tuple((gt_classes >= 0) & (gt_classes < self.num_classes))[0]
+        if self.box_reg_loss_type != "smooth_l1":
+            raise ValueError(f"Invalid bbox reg loss type '{self.box_reg_loss_type}' (this build ships smooth_l1)")
+        fg = (gt_classes >= 0) & (gt_classes < self.num_classes)
+        if not STRICT_BOX_REG_SYNC and pred_deltas.is_cuda and (pred_deltas.shape[1] in (box_dim, box_dim * self.num_classes)) \
+                and box_dim == 4:
+            # one fused kernel (+ a fixed-order reduction): no nonzero(), no assert, no host sync
+            loss, _ = ops.box_reg_loss(proposal_boxes, gt_boxes, pred_deltas, gt_classes, int(self.num_classes),
+                                       [float(v) for v in self.box2box_transform.weights], float(self.smooth_l1_beta),
+                                       bool(pred_deltas.requires_grad and torch.is_grad_enabled()))
+            return loss
+        if not STRICT_BOX_REG_SYNC:
+            # same sum as below, evaluated on every row and masked: no nonzero(), no assert, no host sync
+            if pred_deltas.shape[1] == box_dim:
+                pred = pred_deltas
+            else:
+                cls = gt_classes.clamp(0, self.num_classes - 1)
+                pred = pred_deltas.view(-1, self.num_classes, box_dim)[torch.arange(cls.numel(), device=cls.device), cls]
+            tgt = self.box2box_transform.get_deltas(proposal_boxes, gt_boxes, valid=fg)
+            per = smooth_l1_loss(pred, tgt, self.smooth_l1_beta, reduction="none")
+            loss_box_reg = torch.where(fg[:, None], per, torch.zeros_like(per)).sum()
+            return loss_box_reg / max(gt_classes.numel(), 1.0)
+        fg_inds = nonzero_tuple(fg)[0]
         if pred_deltas.shape[1] == box_dim:
             fg_pred_deltas = pred_deltas[fg_inds]
         else:
             fg_pred_deltas = pred_deltas.view(-1, self.num_classes, box_dim)[fg_inds, gt_classes[fg_inds]]
-        if self.box_reg_loss_type == "smooth_l1":
-            gt_pred_deltas = self.box2box_transform.get_deltas(proposal_boxes[fg_inds], gt_boxes[fg_inds])
-            loss_box_reg = smooth_l1_loss(fg_pred_deltas, gt_pred_deltas, self.smooth_l1_beta, reduction="sum")
-        else:
-            raise ValueError(f"Invalid bbox reg loss type '{self.box_reg_loss_type}' (this build ships smooth_l1)")
+        gt_pred_deltas = self.box2box_transform.get_deltas(proposal_boxes[fg_inds], gt_boxes[fg_inds])
+        loss_box_reg = smooth_l1_loss(fg_pred_deltas, gt_pred_deltas, self.smooth_l1_beta, reduction="sum")
         return loss_box_reg / max(gt_classes.numel(), 1.0)
 
     # ---------------------------------------------------------------- inference (fast_rcnn.py:691-810)

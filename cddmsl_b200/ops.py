@@ -7,7 +7,7 @@ them unchanged.  CUDA only — a CPU tensor raises.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -235,6 +235,52 @@ def _loss_bwd(ctx, gloss, gscores, gdx, gstats):
 
 
 clip_head_loss.register_autograd(_loss_bwd, setup_context=_loss_setup)
+
+
+# ------------------------------------------------------------------------------------ box regression loss
+@torch.library.custom_op("cddmsl_b200::box_reg_loss", mutates_args=(), device_types="cuda")
+def box_reg_loss(proposal_boxes: Tensor, gt_boxes: Tensor, pred_deltas: Tensor, gt: Tensor, num_classes: int,
+                 weights: List[float], beta: float, want_grad: bool) -> Tuple[Tensor, Tensor]:
+    """Smooth-L1 box regression loss over foreground rows / R (fast_rcnn.py:646-689), no host sync.
+    Returns (loss[], d loss / d pred_deltas or empty)."""
+    _lib.require_cuda(pred_deltas, "pred_deltas")
+    pb, gb, pd = _f32c(proposal_boxes), _f32c(gt_boxes), _f32c(pred_deltas)
+    g = gt.to(torch.int64).contiguous()
+    r = pd.shape[0]
+    dev = pd.device
+    agnostic = pd.shape[1] == 4
+    assert agnostic or pd.shape[1] == 4 * num_classes, "pred_deltas must be [R,4] or [R,4K]"
+    assert pb.shape == (r, 4) and gb.shape == (r, 4) and g.numel() == r
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dpred = torch.empty(pd.shape if want_grad else (0,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = torch.empty(int(L.cddmsl_box_reg_loss_workspace_bytes(r)), dtype=torch.uint8, device=dev)
+    wx, wy, ww, wh = [float(v) for v in weights]
+    with torch.cuda.device(dev):
+        _lib.check(L.cddmsl_box_reg_loss(_lib.ptr(pb), _lib.ptr(gb), _lib.ptr(pd), _lib.ptr(g), r, num_classes,
+                                         int(agnostic), wx, wy, ww, wh, beta, None, _lib.ptr(loss),
+                                         _lib.ptr(dpred) if want_grad and r > 0 else None, _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr(dev)), "box_reg_loss")
+    return loss, dpred
+
+
+@box_reg_loss.register_fake
+def _(proposal_boxes, gt_boxes, pred_deltas, gt, num_classes, weights, beta, want_grad):
+    return pred_deltas.new_empty(()), pred_deltas.new_empty(pred_deltas.shape if want_grad else (0,))
+
+
+def _boxreg_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.dtype = inputs[2].dtype
+
+
+def _boxreg_bwd(ctx, gloss, _gd):
+    (dpred,) = ctx.saved_tensors
+    g = (dpred * gloss).to(ctx.dtype) if dpred.numel() else None
+    return None, None, g, None, None, None, None, None
+
+
+box_reg_loss.register_autograd(_boxreg_bwd, setup_context=_boxreg_setup)
 
 
 # ------------------------------------------------------------------------------------ alignment loss

@@ -95,6 +95,18 @@ int cddmsl_clip_head_loss(const float* x, const float* w, const float* w_bg, con
                           const float* grad_scale, int strict_nan, float* scores, float* loss, float* dx,
                           int32_t* stats, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
 
+/* Box-regression loss of the same predictor (fast_rcnn.py:646-689): smooth-L1 (fvcore.nn.smooth_l1_loss, beta)
+ * between pred_deltas and Box2BoxTransform.get_deltas(proposal, gt) (box_regression.py:42-75, weights wx..wh),
+ * summed over foreground rows (0 <= gt_classes < K) and divided by max(R, 1).  pred_deltas is [R,4]
+ * (cls_agnostic != 0) or [R,4K]; dpred (nullable) receives d loss / d pred_deltas * (*grad_scale).  Unlike the
+ * reference there is no device->host sync (no nonzero(), no validity assert): rows outside the foreground are never
+ * evaluated, exactly as upstream never passes them to get_deltas. */
+size_t cddmsl_box_reg_loss_workspace_bytes(int R);
+int cddmsl_box_reg_loss(const float* proposal_boxes, const float* gt_boxes, const float* pred_deltas,
+                        const int64_t* gt_classes, int R, int K, int cls_agnostic, float wx, float wy, float ww,
+                        float wh, float beta, const float* grad_scale, float* loss, float* dpred, void* workspace,
+                        size_t workspace_bytes, cddmsl_stream_t stream);
+
 /* ---------------------------------------------------------------- piece 4: alignment loss ------- */
 /* Row-normalise src|tgt [n_local,D] each (x / |x|, no eps — rcnn.py:308-309, :458-459) and pack them as
  * packed[2][n_local][D] for ONE all-gather per branch (the reference issues two, rcnn.py:455-456;

@@ -192,3 +192,39 @@ def caption_consistency_world(a_locals: List[torch.Tensor], b_locals: List[torch
 def kd_l1_loss(teacher: torch.Tensor, student: torch.Tensor) -> torch.Tensor:
     """rcnn.py:265-272 — L1Loss(teacher.detach(), student) (mean reduction)."""
     return F.l1_loss(teacher.detach(), student)
+
+
+def get_deltas(src_boxes: torch.Tensor, target_boxes: torch.Tensor, weights) -> torch.Tensor:
+    """detectron2/modeling/box_regression.py:42-75 (Box2BoxTransform.get_deltas)."""
+    sw = src_boxes[:, 2] - src_boxes[:, 0]
+    sh = src_boxes[:, 3] - src_boxes[:, 1]
+    sx = src_boxes[:, 0] + 0.5 * sw
+    sy = src_boxes[:, 1] + 0.5 * sh
+    tw = target_boxes[:, 2] - target_boxes[:, 0]
+    th = target_boxes[:, 3] - target_boxes[:, 1]
+    tx = target_boxes[:, 0] + 0.5 * tw
+    ty = target_boxes[:, 1] + 0.5 * th
+    wx, wy, ww, wh = weights
+    assert bool((sw > 0).all()), "Input boxes to Box2BoxTransform are not valid!"
+    return torch.stack((wx * (tx - sx) / sw, wy * (ty - sy) / sh, ww * torch.log(tw / sw), wh * torch.log(th / sh)), dim=1)
+
+
+def smooth_l1_sum(input: torch.Tensor, target: torch.Tensor, beta: float) -> torch.Tensor:
+    """fvcore.nn.smooth_l1_loss(reduction="sum") -- fvcore is a pip dependency of the reference (setup.py:
+    `fvcore>=0.1.5,<0.1.6`), absent from its tree; this is its published definition:
+    |x| < beta: 0.5 x^2 / beta, else |x| - 0.5 beta; beta < 1e-5: plain L1."""
+    n = torch.abs(input - target)
+    if beta < 1e-5:
+        return n.sum()
+    return torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta).sum()
+
+
+def box_reg_loss(proposal_boxes, gt_boxes, pred_deltas, gt_classes, num_classes: int, weights, beta: float):
+    """fast_rcnn.py:646-689 (smooth_l1 branch): foreground rows only, normalised by the number of RoIs."""
+    fg = ((gt_classes >= 0) & (gt_classes < num_classes)).nonzero(as_tuple=True)[0]
+    if pred_deltas.shape[1] == 4:
+        fg_pred = pred_deltas[fg]
+    else:
+        fg_pred = pred_deltas.view(-1, num_classes, 4)[fg, gt_classes[fg]]
+    tgt = get_deltas(proposal_boxes[fg], gt_boxes[fg], weights)
+    return smooth_l1_sum(fg_pred, tgt, beta) / max(gt_classes.numel(), 1.0)

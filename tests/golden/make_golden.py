@@ -14,6 +14,9 @@ What it records (all seeded, fp32 / int64):
     `GatherLayer` (`detectron2/modeling/backbone/clipcap/gather.py`, loaded verbatim) under a real
     2-process gloo group, which pins the gather/backward semantics of `caption_consistency_world`.
 
+  * box_reg.npz — `Box2BoxTransform.get_deltas` of the reference (`detectron2/modeling/box_regression.py`, loaded
+    verbatim with its unused imports stubbed) + fvcore's published smooth-L1 (fvcore is not vendored).
+
 The tests never read /root/reference; they read these files.
 """
 import importlib.util
@@ -35,6 +38,7 @@ from oracle import torch_ref  # noqa: E402
 def load_by_path(name, rel):
     spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
     mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod  # torch.jit.script (box_regression.py) inspects the defining module
     spec.loader.exec_module(mod)
     return mod
 
@@ -190,11 +194,62 @@ def align_cases():
     print("align: single + world2 (real GatherLayer under gloo agrees with the emulation)")
 
 
+def box_reg_cases():
+    """get_deltas comes from the reference's own Box2BoxTransform (detectron2/modeling/box_regression.py, loaded
+    verbatim; its imports of fvcore / detectron2.layers / detectron2.structures are stubbed, get_deltas uses none of
+    them); the smooth-L1 reduction is fvcore's published definition (oracle/torch_ref.py:smooth_l1_sum)."""
+    import types
+
+    stubs = {}
+    for name, attrs in {"fvcore": {}, "fvcore.nn": {"giou_loss": None, "smooth_l1_loss": None},
+                        "detectron2": {}, "detectron2.layers": {"cat": torch.cat},
+                        "detectron2.structures": {"Boxes": object}}.items():
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+            stubs[name] = m
+    try:
+        ref = load_by_path("ref_box_regression", "detectron2/modeling/box_regression.py")
+    finally:
+        for name in stubs:
+            sys.modules.pop(name, None)
+    weights = (10.0, 10.0, 5.0, 5.0)
+    b2b = ref.Box2BoxTransform(weights=weights)
+    g = synth.generator(15)
+    r, k = 300, 7
+    prop = synth.make_boxes(r, 600, 1000, g, degenerate_frac=0.0)
+    gtb = synth.make_boxes(r, 600, 1000, g, degenerate_frac=0.0)
+    gt = torch.randint(0, k + 1, (r,), generator=g)
+    bg = (gt == k).nonzero()[:6, 0]
+    prop[bg] = torch.tensor([5.0, 5.0, 5.0, 5.0])                    # degenerate background proposals: never evaluated
+    fg = ((gt >= 0) & (gt < k)).nonzero(as_tuple=True)[0]
+    ref_deltas = b2b.get_deltas(prop[fg], gtb[fg])
+    out = dict(prop=prop.numpy(), gtb=gtb.numpy(), gt=gt.numpy(), fg=fg.numpy(), ref_deltas=ref_deltas.numpy(),
+               weights=np.array(weights, dtype=np.float64), k=np.array([k]))
+    for tag, width, beta in (("agnostic", 4, 0.5), ("perclass", 4 * k, 0.5), ("l1", 4, 0.0)):
+        pred = torch.randn(r, width, generator=g).requires_grad_(True)
+        fg_pred = pred[fg] if width == 4 else pred.view(-1, k, 4)[fg, gt[fg]]
+        loss = torch_ref.smooth_l1_sum(fg_pred, ref_deltas, beta) / max(r, 1.0)
+        loss.backward()
+        out[f"pred_{tag}"] = pred.detach().numpy()
+        out[f"beta_{tag}"] = np.array([beta])
+        out[f"loss_{tag}"] = np.array([loss.item()], dtype=np.float32)
+        out[f"dpred_{tag}"] = pred.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "box_reg.npz"), **out)
+    print("box_reg: agnostic perclass l1")
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
+    if len(sys.argv) > 1 and sys.argv[1] == "box_reg":
+        box_reg_cases()
+        sys.exit(0)
     roi_cases()
     nms_cases()
     head_cases()
     align_cases()
+    box_reg_cases()
     sizes = {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")}
     print(sizes, sum(sizes.values()))

@@ -209,3 +209,52 @@ def test_empty_batch_and_box_reg_and_inference():
     assert torch.equal(res[0].pred_classes.cpu(), inds[keep][:, 1])
     assert torch.allclose(res[0].scores.cpu(), probs[:, :-1][mask][keep], rtol=1e-6)
     assert torch.equal(kept[0].cpu(), inds[keep][:, 0])
+
+
+@pytest.mark.parametrize("tag", ["agnostic", "perclass", "l1"])
+def test_box_reg_loss_fixture(golden_dir, tag):
+    """Fused box-regression loss through the C ABI vs the fixture built on the reference's get_deltas
+    (fast_rcnn.py:646-689, box_regression.py:42-75).  fp32: 1e-5 forward, 1e-4 backward."""
+    from cddmsl_b200 import ops
+
+    f = np.load(os.path.join(golden_dir, "box_reg.npz"))
+    prop, gtb, gt = (torch.from_numpy(f[k]).to(DEV) for k in ("prop", "gtb", "gt"))
+    pred = torch.from_numpy(f[f"pred_{tag}"]).to(DEV).requires_grad_(True)
+    w = [float(v) for v in f["weights"]]
+    loss, _ = ops.box_reg_loss(prop, gtb, pred, gt, int(f["k"][0]), w, float(f[f"beta_{tag}"][0]), True)
+    (loss * 3.0).backward()
+    _close(loss.item(), float(f[f"loss_{tag}"][0]), 1e-5, "loss")
+    _close(pred.grad.cpu().numpy(), 3.0 * f[f"dpred_{tag}"], 1e-4, "dpred")
+    assert torch.isfinite(pred.grad).all()      # degenerate background proposals are never evaluated
+
+
+def test_box_reg_loss_through_predictor_matches_oracle_and_is_sync_free():
+    import cddmsl_b200.modeling.fast_rcnn as fr
+
+    cfg = synth.CONFIGS["tiny"]
+    g = synth.generator(21)
+    x, w, w_bg, gt = synth.make_head_inputs(cfg, g, n_rois=128)
+    boxes = synth.make_boxes(128, 600, 1000, g, degenerate_frac=0.0)
+    m = _predictor(cfg.num_classes, cfg.emb_dim, w)
+    xx = x.to(DEV).requires_grad_(True)
+    scores, deltas = m(xx)
+    props = _proposals(gt, boxes)
+    out = m.losses((scores, deltas), props)
+    ref = torch_ref.box_reg_loss(boxes, boxes + 3.0, deltas.detach().cpu(), gt, cfg.num_classes,
+                                 m.box2box_transform.weights, m.smooth_l1_beta)
+    _close(out["loss_box_reg"].item(), ref.item(), 1e-5, "loss_box_reg")
+    out["loss_box_reg"].backward()
+    assert m.bbox_pred.weight.grad is not None and torch.isfinite(m.bbox_pred.weight.grad).all()
+    # the strict (reference-shaped, syncing) evaluation gives the same number
+    fr.STRICT_BOX_REG_SYNC = True
+    try:
+        strict = m.losses((scores.detach(), deltas.detach()), props)["loss_box_reg"].item()
+    finally:
+        fr.STRICT_BOX_REG_SYNC = False
+    _close(out["loss_box_reg"].item(), strict, 1e-5, "strict")
+    # empty batch
+    z, _ = __import__("cddmsl_b200").ops.box_reg_loss(torch.zeros(0, 4, device=DEV), torch.zeros(0, 4, device=DEV),
+                                                      torch.zeros(0, 4, device=DEV),
+                                                      torch.zeros(0, dtype=torch.int64, device=DEV), 3,
+                                                      [10.0, 10.0, 5.0, 5.0], 0.5, True)
+    assert z.item() == 0.0

@@ -1,5 +1,6 @@
 """CPU: host-side logic of the mirror (no kernels): pooler box format, sharding, GatherLayer under a real
 world_size-2 gloo group, box transform, containers, the PyTorch-arithmetic loss helpers."""
+import math
 import os
 
 import numpy as np
@@ -146,3 +147,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_box_reg_loss_masked_equals_reference_selection():
+    """fast_rcnn.py:646-689: the sync-free masked evaluation gives the loss and gradient of the nonzero()-selected one,
+    also with degenerate background proposals (which the reference never feeds to get_deltas)."""
+    import cddmsl_b200.modeling.fast_rcnn as fr
+    from cddmsl_b200.modeling import Box2BoxTransform
+
+    g = torch.Generator().manual_seed(5)
+    R, K = 200, 7
+    boxes = synth.make_boxes(R, 600, 1000, g, degenerate_frac=0.0)
+    gt_boxes = synth.make_boxes(R, 600, 1000, g, degenerate_frac=0.0)
+    gt = torch.randint(0, K + 1, (R,), generator=g)
+    bg_rows = (gt == K).nonzero()[:5, 0]
+    boxes[bg_rows] = torch.tensor([10.0, 10.0, 10.0, 10.0])       # zero-area background rows
+    for agnostic in (True, False):
+        m = object.__new__(fr.FastRCNNOutputLayers)
+        m.num_classes, m.box_reg_loss_type, m.smooth_l1_beta = K, "smooth_l1", 0.5
+        m.box2box_transform = Box2BoxTransform((10.0, 10.0, 5.0, 5.0))
+        deltas = torch.randn(R, 4 if agnostic else 4 * K, generator=g)
+        res = []
+        for strict in (True, False):
+            fr.STRICT_BOX_REG_SYNC = strict
+            try:
+                d = deltas.clone().requires_grad_(True)
+                l = m.box_reg_loss(boxes, gt_boxes, d, gt)
+                l.backward()
+                res.append((l.item(), d.grad.clone()))
+            finally:
+                fr.STRICT_BOX_REG_SYNC = False
+        assert math.isfinite(res[1][0])
+        assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[0][0])
+        assert torch.allclose(res[0][1], res[1][1], rtol=1e-6, atol=1e-8)

@@ -169,3 +169,25 @@ def test_focal_saturation_nan_is_a_reference_property():
     loss = torch_ref.focal_loss(s, torch.tensor([0]), 2, 0.5, 0.2)
     loss.backward()
     assert loss.item() == 0.0 and torch.isnan(s.grad).all()
+
+
+def test_box_reg_oracle_matches_reference_get_deltas_fixture(golden_dir):
+    """box_reg.npz: get_deltas from the reference's own Box2BoxTransform (box_regression.py:42-75)."""
+    f = np.load(os.path.join(golden_dir, "box_reg.npz"))
+    prop, gtb, gt = torch.from_numpy(f["prop"]), torch.from_numpy(f["gtb"]), torch.from_numpy(f["gt"])
+    fg = torch.from_numpy(f["fg"])
+    w = tuple(float(v) for v in f["weights"])
+    k = int(f["k"][0])
+    d = torch_ref.get_deltas(prop[fg], gtb[fg], w)
+    assert np.array_equal(d.numpy(), f["ref_deltas"])          # same fp32 arithmetic, same order: bit-equal
+    for tag in ("agnostic", "perclass", "l1"):
+        pred = torch.from_numpy(f[f"pred_{tag}"]).requires_grad_(True)
+        loss = torch_ref.box_reg_loss(prop, gtb, pred, gt, k, w, float(f[f"beta_{tag}"][0]))
+        loss.backward()
+        assert abs(loss.item() - float(f[f"loss_{tag}"][0])) <= 1e-6 * abs(loss.item())
+        assert np.allclose(pred.grad.numpy(), f[f"dpred_{tag}"], rtol=1e-6, atol=0)
+    # the reference asserts on degenerate FOREGROUND proposals (box_regression.py:74)
+    bad = prop.clone()
+    bad[fg[0]] = torch.tensor([3.0, 3.0, 3.0, 9.0])
+    with pytest.raises(AssertionError):
+        torch_ref.box_reg_loss(bad, gtb, torch.zeros(len(gt), 4), gt, k, w, 0.5)
