@@ -12,9 +12,14 @@
 //   5. greedy scan on the device: per 64-box block a warp-ballot fix-point resolves the diagonal tile, the
 //      kept rows (mask words prefetched one block ahead) are OR-ed into the removed-bitmap, kept indices are
 //      emitted in order                                                    -> nms_scan_kernel
+// Every kernel takes an image index from the grid (blockIdx.z, or .x for the one-CTA-per-image kernels) and a
+// per-image box count read from device memory, so ONE launch sequence serves the B images of an RPN batch
+// (cddmsl_nms_batched: padded [B][Mmax] layout, counts on the device, no host sync; the B serial greedy scans
+// run concurrently on B SMs).  cddmsl_nms is the B = 1 case.
 // IoU arithmetic is fp32 without FMA contraction ((area_i + area_j) - inter, IEEE division) and the
 // threshold test promotes the fp32 IoU to double, exactly like the CPU kernel (oracle/c/nms_ref.c).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -23,9 +28,19 @@ namespace cddmsl {
 
 constexpr int kTile = 64;
 
-__global__ void nms_max_kernel(const float* __restrict__ boxes, int64_t n4, float* __restrict__ out_max) {
-  // single block; M*4 values.  -inf start; result is the exact max (order-independent).
+// per-image box count: device array (batched entry point) or the host-known M
+__device__ __forceinline__ int image_count(const int32_t* __restrict__ counts, int img, int m_fixed, int m_max) {
+  return counts ? min(max(counts[img], 0), m_max) : m_fixed;
+}
+
+__global__ void nms_max_kernel(const float* __restrict__ boxes_all, const int32_t* __restrict__ counts, int m_fixed,
+                               int m_max, float* __restrict__ out_max_all) {
+  // one block per image; M*4 values.  -inf start; result is the exact max (order-independent).
   __shared__ float red[32];
+  const int img = blockIdx.x;
+  const float* boxes = boxes_all + (size_t)img * m_max * 4;
+  float* out_max = out_max_all + img;
+  const int64_t n4 = (int64_t)image_count(counts, img, m_fixed, m_max) * 4;
   float m = -INFINITY;
   for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) m = fmaxf(m, boxes[i]);
   m = warp_max(m);
@@ -39,20 +54,38 @@ __global__ void nms_max_kernel(const float* __restrict__ boxes, int64_t n4, floa
 }
 
 __global__ void nms_iota_kernel(const float* __restrict__ scores, float* __restrict__ keys, int* __restrict__ vals,
-                                int M) {
+                                const int32_t* __restrict__ counts, int m_fixed, int m_max,
+                                int* __restrict__ seg_begin, int* __restrict__ seg_end) {
+  const int img = blockIdx.z;
+  const int M = image_count(counts, img, m_fixed, m_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && seg_begin) {  // segment [img*m_max, img*m_max + M) of the padded arrays
+    seg_begin[img] = img * m_max;
+    seg_end[img] = img * m_max + M;
+  }
   if (i < M) {
-    float s = scores[i];
-    keys[i] = (s == 0.f) ? 0.f : s;  // -0.0 and +0.0 compare equal in the reference's sort
-    vals[i] = i;
+    const size_t g = (size_t)img * m_max + i;
+    float s = scores[g];
+    keys[g] = (s == 0.f) ? 0.f : s;  // -0.0 and +0.0 compare equal in the reference's sort
+    vals[g] = i;
   }
 }
 
-__global__ void nms_gather_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ idxs,
-                                  const int* __restrict__ order, const float* __restrict__ max_coord,
-                                  int coord_trick, float4* __restrict__ sboxes, int* __restrict__ scls, int M) {
+__global__ void nms_gather_kernel(const float4* __restrict__ boxes_all, const int64_t* __restrict__ idxs_all,
+                                  const int* __restrict__ order_all, const float* __restrict__ max_coord_all,
+                                  int coord_trick, float4* __restrict__ sboxes_all, int* __restrict__ scls_all,
+                                  const int32_t* __restrict__ counts, int m_fixed, int m_max) {
+  const int img = blockIdx.z;
+  const int M = image_count(counts, img, m_fixed, m_max);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
+  const size_t ib = (size_t)img * m_max;
+  const float4* boxes = boxes_all + ib;
+  const int64_t* idxs = idxs_all ? idxs_all + ib : nullptr;
+  const int* order = order_all + ib;
+  const float* max_coord = max_coord_all + img;
+  float4* sboxes = sboxes_all + ib;
+  int* scls = scls_all + ib;
   const int o = order[i];
   float4 b = boxes[o];
   int cls = 0;
@@ -87,10 +120,18 @@ __device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float a
 // Diagonal tiles additionally emit the COLUMN view through warp ballots: coldiag[rb*64+j] bit i = row i (< j, same
 // tile) suppresses j — what the scan kernel's ballot fix-point needs.
 __global__ void __launch_bounds__(kTile)
-nms_mask_kernel(const float4* __restrict__ sboxes, const int* __restrict__ scls, int M, double thr, int col_blocks,
-                unsigned long long* __restrict__ mask, unsigned long long* __restrict__ coldiag) {
+nms_mask_kernel(const float4* __restrict__ sboxes_all, const int* __restrict__ scls_all,
+                const int32_t* __restrict__ counts, int m_fixed, int m_max, double thr, int col_blocks,
+                unsigned long long* __restrict__ mask_all, unsigned long long* __restrict__ coldiag_all) {
+  // col_blocks = ceil(m_max / 64): row stride of the mask for every image
+  const int img = blockIdx.z;
+  const int M = image_count(counts, img, m_fixed, m_max);
   const int rb = blockIdx.y, cb = blockIdx.x;
-  if (cb < rb) return;
+  if (cb < rb || cb * kTile >= M) return;
+  const float4* sboxes = sboxes_all + (size_t)img * m_max;
+  const int* scls = scls_all + (size_t)img * m_max;
+  unsigned long long* mask = mask_all + (size_t)img * m_max * col_blocks;
+  unsigned long long* coldiag = coldiag_all + (size_t)img * col_blocks * kTile;
   __shared__ float4 cbox[kTile];
   __shared__ float carea[kTile];
   __shared__ int ccls[kTile];
@@ -138,10 +179,18 @@ nms_mask_kernel(const float4* __restrict__ sboxes, const int* __restrict__ scls,
 //     block ahead (the loads do not depend on the scan state), so applying the kept rows to the removed-bitmap is
 //     register work; column words beyond the first 256 are fetched in batches of 16 independent loads.
 __global__ void __launch_bounds__(1024)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long long* __restrict__ coldiag,
-                const int* __restrict__ order, int M, int col_blocks, int64_t* __restrict__ keep,
-                int32_t* __restrict__ num_keep) {
-  extern __shared__ unsigned long long remv[];  // [col_blocks]
+nms_scan_kernel(const unsigned long long* __restrict__ mask_all, const unsigned long long* __restrict__ coldiag_all,
+                const int* __restrict__ order_all, const int32_t* __restrict__ counts, int m_fixed, int m_max,
+                int stride_blocks, int64_t* __restrict__ keep_all, int32_t* __restrict__ num_keep_all) {
+  extern __shared__ unsigned long long remv[];  // [stride_blocks]
+  const int img = blockIdx.x;
+  const int M = image_count(counts, img, m_fixed, m_max);
+  const int col_blocks = (M + kTile - 1) / kTile;  // this image's blocks; rows are stride_blocks words apart
+  const unsigned long long* mask = mask_all + (size_t)img * m_max * stride_blocks;
+  const unsigned long long* coldiag = coldiag_all + (size_t)img * stride_blocks * kTile;
+  const int* order = order_all + (size_t)img * m_max;
+  int64_t* keep = keep_all + (size_t)img * m_max;
+  int32_t* num_keep = num_keep_all + img;
   __shared__ unsigned long long kept_s;
   __shared__ int count_s;
   for (int w = threadIdx.x; w < col_blocks; w += blockDim.x) remv[w] = 0ull;
@@ -155,12 +204,12 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
 #define NMS_LOAD_ROWS(B, WORD, V)                                                             \
   _Pragma("unroll") for (int u = 0; u < 16; ++u) {                                            \
     const int row_ = (B) * kTile + 4 * u + slot;                                              \
-    (V)[u] = ((WORD) < col_blocks && row_ < M) ? mask[(size_t)row_ * col_blocks + (WORD)] : 0ull; \
+    (V)[u] = ((WORD) < col_blocks && row_ < M) ? mask[(size_t)row_ * stride_blocks + (WORD)] : 0ull; \
   }
   unsigned long long v[16];  // prefetched for the block about to be resolved
   NMS_LOAD_ROWS(0, 1 + wlane, v)
   unsigned long long cm_lo = 0ull, cm_hi = 0ull;  // column masks of block 0 for warp 0
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < 32 && col_blocks > 0) {
     cm_lo = coldiag[lane];
     cm_hi = coldiag[lane + 32];
   }
@@ -233,6 +282,8 @@ struct NmsWs {
   float4* sboxes;
   int* scls;
   float* max_coord;
+  int* seg_begin;
+  int* seg_end;
   unsigned long long* mask;
   unsigned long long* coldiag;
   void* cub_temp;
@@ -240,7 +291,7 @@ struct NmsWs {
   size_t total;
 };
 
-static NmsWs carve(void* base, int64_t M) {
+static NmsWs carve(void* base, int64_t B, int64_t M) {
   NmsWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -248,30 +299,82 @@ static NmsWs carve(void* base, int64_t M) {
     off += align_up(bytes, 256);
     return p;
   };
+  const size_t b = (size_t)(B > 0 ? B : 1);
   const size_t m = (size_t)(M > 0 ? M : 1);
   const size_t cb = (m + kTile - 1) / kTile;
-  w.keys_in = (float*)take(m * 4);
-  w.keys_out = (float*)take(m * 4);
-  w.vals_in = (int*)take(m * 4);
-  w.order = (int*)take(m * 4);
-  w.sboxes = (float4*)take(m * 16);
-  w.scls = (int*)take(m * 4);
-  w.max_coord = (float*)take(4);
-  w.mask = (unsigned long long*)take(m * cb * 8);
-  w.coldiag = (unsigned long long*)take(cb * kTile * 8);
+  w.keys_in = (float*)take(b * m * 4);
+  w.keys_out = (float*)take(b * m * 4);
+  w.vals_in = (int*)take(b * m * 4);
+  w.order = (int*)take(b * m * 4);
+  w.sboxes = (float4*)take(b * m * 16);
+  w.scls = (int*)take(b * m * 4);
+  w.max_coord = (float*)take(b * 4);
+  w.seg_begin = (int*)take(b * 4);
+  w.seg_end = (int*)take(b * 4);
+  w.mask = (unsigned long long*)take(b * m * cb * 8);
+  w.coldiag = (unsigned long long*)take(b * cb * kTile * 8);
   w.cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float*)nullptr, (float*)nullptr,
-                                            (const int*)nullptr, (int*)nullptr, (int)m, 0, 32, (cudaStream_t)0);
+  if (b == 1) {
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float*)nullptr, (float*)nullptr,
+                                              (const int*)nullptr, (int*)nullptr, (int)m, 0, 32, (cudaStream_t)0);
+  } else {
+    cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float*)nullptr, (float*)nullptr,
+                                                       (const int*)nullptr, (int*)nullptr, (int)(b * m), (int)b,
+                                                       (const int*)nullptr, (const int*)nullptr, 0, 32,
+                                                       (cudaStream_t)0);
+  }
   w.cub_temp = take(w.cub_bytes);
   w.total = off;
   return w;
+}
+
+// B images, padded to m_max boxes each; counts == nullptr: every image holds exactly m_max boxes (the B = 1 call)
+static int nms_run(const float* boxes, const float* scores, const int64_t* idxs, const int32_t* counts, int B,
+                   int m_max, double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep, const NmsWs& w,
+                   cudaStream_t stream) {
+  const int col_blocks = ceil_div(m_max, kTile);
+  if ((size_t)col_blocks * 8 > 200 * 1024) return CDDMSL_EINVAL;  // removed-bitmap must fit shared memory
+  if (idxs && coord_trick) {
+    nms_max_kernel<<<B, 1024, 0, stream>>>(boxes, counts, m_max, m_max, w.max_coord);
+    count_launch();
+  }
+  nms_iota_kernel<<<dim3(ceil_div(m_max, 256), 1, B), 256, 0, stream>>>(scores, w.keys_in, w.vals_in, counts, m_max,
+                                                                        m_max, counts ? w.seg_begin : nullptr,
+                                                                        w.seg_end);
+  count_launch();
+  size_t cub_bytes = w.cub_bytes;
+  if (!counts) {  // B == 1, host-known size
+    CDDMSL_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cub_bytes, w.keys_in, w.keys_out, w.vals_in,
+                                                          w.order, m_max, 0, 32, stream));
+  } else {
+    CDDMSL_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(w.cub_temp, cub_bytes, w.keys_in, w.keys_out,
+                                                                   w.vals_in, w.order, B * m_max, B, w.seg_begin,
+                                                                   w.seg_end, 0, 32, stream));
+  }
+  count_launch(3);  // histogram + onesweep passes (CUB internal; counted as one logical sort)
+  nms_gather_kernel<<<dim3(ceil_div(m_max, 256), 1, B), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(boxes), idxs, w.order, w.max_coord, coord_trick, w.sboxes, w.scls, counts,
+      m_max, m_max);
+  count_launch();
+  nms_mask_kernel<<<dim3(col_blocks, col_blocks, B), kTile, 0, stream>>>(w.sboxes, w.scls, counts, m_max, m_max,
+                                                                         iou_threshold, col_blocks, w.mask,
+                                                                         w.coldiag);
+  count_launch();
+  const int smem = col_blocks * 8;
+  if (smem > 48 * 1024)
+    CDDMSL_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  nms_scan_kernel<<<B, 1024, smem, stream>>>(w.mask, w.coldiag, w.order, counts, m_max, m_max, col_blocks, keep,
+                                             num_keep);
+  count_launch();
+  CDDMSL_CHECK_LAUNCH();
+  return CDDMSL_OK;
 }
 
 }  // namespace cddmsl
 
 using namespace cddmsl;
 
-extern "C" size_t cddmsl_nms_workspace_bytes(int64_t M) { return carve(nullptr, M).total; }
+extern "C" size_t cddmsl_nms_workspace_bytes(int64_t M) { return carve(nullptr, 1, M).total; }
 
 extern "C" int cddmsl_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
                           double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep, void* workspace,
@@ -286,32 +389,32 @@ extern "C" int cddmsl_nms(const float* boxes, const float* scores, const int64_t
   if (!boxes || !scores || !keep || !workspace) return CDDMSL_EINVAL;
   if ((reinterpret_cast<uintptr_t>(boxes) & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
     return CDDMSL_EALIGN;
-  NmsWs w = carve(workspace, M);
+  NmsWs w = carve(workspace, 1, M);
   if (w.total > workspace_bytes) return CDDMSL_EWORKSPACE;
-  const int m = (int)M;
-  const int col_blocks = ceil_div(m, kTile);
-  if ((size_t)col_blocks * 8 > 200 * 1024) return CDDMSL_EINVAL;  // removed-bitmap must fit shared memory
+  return nms_run(boxes, scores, idxs, nullptr, 1, (int)M, iou_threshold, coord_trick, keep, num_keep, w, stream);
+}
 
-  if (idxs && coord_trick) {
-    nms_max_kernel<<<1, 1024, 0, stream>>>(boxes, (int64_t)m * 4, w.max_coord);
-    count_launch();
+extern "C" size_t cddmsl_nms_batched_workspace_bytes(int B, int64_t Mmax) {
+  return carve(nullptr, B < 2 ? 2 : B, Mmax).total;
+}
+
+extern "C" int cddmsl_nms_batched(const float* boxes, const float* scores, const int64_t* idxs,
+                                  const int32_t* counts, int B, int64_t Mmax, double iou_threshold, int coord_trick,
+                                  int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                                  cddmsl_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (B < 0 || Mmax < 0 || (B > 0 && !num_keep)) return CDDMSL_EINVAL;
+  if (B == 0) return CDDMSL_OK;
+  if (Mmax == 0) {
+    CDDMSL_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t) * B, stream));
+    return CDDMSL_OK;
   }
-  nms_iota_kernel<<<ceil_div(m, 256), 256, 0, stream>>>(scores, w.keys_in, w.vals_in, m);
-  count_launch();
-  CDDMSL_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, w.cub_bytes, w.keys_in, w.keys_out, w.vals_in,
-                                                        w.order, m, 0, 32, stream));
-  count_launch(3);  // histogram + onesweep passes (CUB internal; counted as one logical sort)
-  nms_gather_kernel<<<ceil_div(m, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(boxes), idxs, w.order,
-                                                           w.max_coord, coord_trick, w.sboxes, w.scls, m);
-  count_launch();
-  nms_mask_kernel<<<dim3(col_blocks, col_blocks), kTile, 0, stream>>>(w.sboxes, w.scls, m, iou_threshold,
-                                                                      col_blocks, w.mask, w.coldiag);
-  count_launch();
-  const int smem = col_blocks * 8;
-  if (smem > 48 * 1024)
-    CDDMSL_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  nms_scan_kernel<<<1, 1024, smem, stream>>>(w.mask, w.coldiag, w.order, m, col_blocks, keep, num_keep);
-  count_launch();
-  CDDMSL_CHECK_LAUNCH();
-  return CDDMSL_OK;
+  if (Mmax > (1 << 24) || (int64_t)B * Mmax > (1ll << 30) || B > 65535) return CDDMSL_EINVAL;
+  if (!boxes || !scores || !keep || !workspace || !counts) return CDDMSL_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(boxes) & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return CDDMSL_EALIGN;
+  const int bw = B < 2 ? 2 : B;  // the segmented sort also serves B == 1 with a device-side count
+  NmsWs w = carve(workspace, bw, Mmax);
+  if (w.total > workspace_bytes) return CDDMSL_EWORKSPACE;
+  return nms_run(boxes, scores, idxs, counts, B, (int)Mmax, iou_threshold, coord_trick, keep, num_keep, w, stream);
 }

@@ -1,15 +1,59 @@
 """`find_top_rpn_proposals` (detectron2/modeling/proposal_generator/proposal_utils.py:22-130): the RPN call
 site of `batched_nms`.  Per feature level take the pre-NMS top-k by objectness, then per image: finite
 check, clip, drop empty boxes, level-aware NMS, post-NMS top-k.  Same control flow as upstream (including
-the FloatingPointError in training); only the NMS underneath is the sm_100a kernel."""
+the FloatingPointError in training); only the NMS underneath is the sm_100a kernel.
+
+On CUDA inputs the per-image loop is evaluated for all images at once (`_per_image_batched`): masks instead of
+data-dependent indexing, a stable partition instead of boolean selection, ONE batched NMS call and ONE device->host
+read for the whole batch (upstream: three syncs and one NMS per image).  Results are identical to the loop."""
 from __future__ import annotations
 
 from typing import List, Tuple
 
 import torch
 
-from ..layers import batched_nms, cat
+from ..layers import batched_nms, batched_nms_images, cat
 from ..structures import Boxes, Instances
+
+
+BATCHED_IMAGES = True  # False: the upstream-shaped per-image loop (one NMS launch sequence + syncs per image)
+
+
+def _per_image_batched(topk_proposals, topk_scores, level_ids, image_sizes, nms_thresh, post_nms_topk, min_box_size,
+                       training):
+    """proposal_utils.py:42-66 for every image at once.  topk_proposals [N,M,4], topk_scores [N,M], level_ids [M]."""
+    n_img, m = topk_scores.shape
+    device = topk_scores.device
+    boxes = topk_proposals.float()
+    valid = torch.isfinite(boxes).all(dim=2) & torch.isfinite(topk_scores)
+    hw = torch.tensor([[float(h), float(w)] for h, w in image_sizes], device=device)        # Boxes.clip, boxes.py:192-206
+    h, w = hw[:, 0:1], hw[:, 1:2]
+    zero = torch.zeros((), device=device)
+    x1 = torch.minimum(torch.maximum(boxes[..., 0], zero), w)
+    y1 = torch.minimum(torch.maximum(boxes[..., 1], zero), h)
+    x2 = torch.minimum(torch.maximum(boxes[..., 2], zero), w)
+    y2 = torch.minimum(torch.maximum(boxes[..., 3], zero), h)
+    boxes = torch.stack((x1, y1, x2, y2), dim=-1)
+    nonempty = ((x2 - x1) > min_box_size) & ((y2 - y1) > min_box_size)                      # Boxes.nonempty, boxes.py:208-222
+    sel = valid & nonempty
+    # boolean selection == stable partition (selected rows first, original order) + a count
+    perm = torch.argsort((~sel).to(torch.int8), dim=1, stable=True)
+    boxes = torch.gather(boxes, 1, perm.unsqueeze(-1).expand(-1, -1, 4)).contiguous()
+    scores = torch.gather(topk_scores, 1, perm)
+    lvl = level_ids.to(torch.int64)[perm]
+    counts = sel.sum(dim=1).to(torch.int32)
+    keep, num_keep = batched_nms_images(boxes, scores, lvl, counts, nms_thresh)
+    host = torch.cat([num_keep, valid.all().reshape(1).to(torch.int32)]).tolist()          # the one sync of the batch
+    if training and not host[-1]:
+        raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+    results: List[Instances] = []
+    for n, image_size in enumerate(image_sizes):
+        k = keep[n, : min(int(host[n]), post_nms_topk)]
+        res = Instances(image_size)
+        res.proposal_boxes = Boxes(boxes[n][k])
+        res.objectness_logits = scores[n][k]
+        results.append(res)
+    return results
 
 
 def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits: List[torch.Tensor],
@@ -38,6 +82,9 @@ def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits
     topk_proposals = cat(topk_proposals, dim=1)
     level_ids = cat(level_ids, dim=0)
 
+    if BATCHED_IMAGES and device.type == "cuda" and num_images > 0:
+        return _per_image_batched(topk_proposals, topk_scores, level_ids, image_sizes, nms_thresh, post_nms_topk,
+                                  min_box_size, training)
     results: List[Instances] = []
     for n, image_size in enumerate(image_sizes):
         boxes = Boxes(topk_proposals[n])

@@ -121,6 +121,37 @@ def _(boxes, scores, idxs, iou_threshold, coord_trick):
     return boxes.new_empty((n,), dtype=torch.int64)
 
 
+@torch.library.custom_op("cddmsl_b200::nms_images", mutates_args=(), device_types="cuda")
+def nms_images(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], counts: Tensor, iou_threshold: float,
+               coord_trick: bool) -> Tuple[Tensor, Tensor]:
+    """NMS of B images in one launch sequence.  boxes [B,M,4], scores [B,M], idxs [B,M] or None, counts int32 [B]
+    (device; image b uses its first counts[b] rows).  Returns (keep int64 [B,M], num_keep int32 [B]): keep[b, :num_keep[b]]
+    are the kept row indices of image b in score order.  No host sync here -- the caller decides when to read."""
+    _lib.require_cuda(boxes, "boxes")
+    b = _f32c(boxes)
+    s = _f32c(scores)
+    nb, m = s.shape
+    assert b.shape == (nb, m, 4) and counts.numel() == nb
+    keep = torch.empty((nb, m), dtype=torch.int64, device=b.device)
+    nk = torch.zeros((nb,), dtype=torch.int32, device=b.device)
+    if nb == 0 or m == 0:
+        return keep, nk
+    ids = None if idxs is None else idxs.to(torch.int64).contiguous()
+    cnt = counts.to(device=b.device, dtype=torch.int32).contiguous()
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_nms_batched_workspace_bytes(nb, m), b.device)
+    with torch.cuda.device(b.device):
+        _lib.check(L.cddmsl_nms_batched(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), _lib.ptr(cnt), nb, m,
+                                        float(iou_threshold), int(coord_trick), _lib.ptr(keep), _lib.ptr(nk),
+                                        _lib.ptr(ws), ws.numel(), _lib.stream_ptr(b.device)), "nms_batched")
+    return keep, nk
+
+
+@nms_images.register_fake
+def _(boxes, scores, idxs, counts, iou_threshold, coord_trick):
+    return scores.new_empty(scores.shape, dtype=torch.int64), scores.new_empty((scores.shape[0],), dtype=torch.int32)
+
+
 # ------------------------------------------------------------------------------------------ CLIP head
 def _head_ws(r, d, k, device):
     return _ws(_lib.lib().cddmsl_clip_head_workspace_bytes(r, d, k), device)

@@ -69,6 +69,17 @@ int cddmsl_nms(const float* boxes, const float* scores, const int64_t* idxs, int
                int coord_trick, int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
                cddmsl_stream_t stream);
 
+/* The B images of one RPN batch in one call (the loop of proposal_utils.py:42-66 calls batched_nms once per image).
+ * Padded layout: boxes [B][Mmax][4], scores [B][Mmax], idxs [B][Mmax] (nullable), counts int32[B] ON THE DEVICE
+ * (image b holds counts[b] <= Mmax boxes; the rest of its slice is ignored), keep int64[B][Mmax] (indices local to
+ * the image, score order), num_keep int32[B].  Result per image is bit-identical to cddmsl_nms on that image's
+ * first counts[b] boxes; the coordinate-trick offset uses that image's own max coordinate (boxes.py:67-73).
+ * No host synchronisation; the B greedy scans run concurrently. */
+size_t cddmsl_nms_batched_workspace_bytes(int B, int64_t Mmax);
+int cddmsl_nms_batched(const float* boxes, const float* scores, const int64_t* idxs, const int32_t* counts, int B,
+                       int64_t Mmax, double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep,
+                       void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+
 /* ---------------------------------------------------------------- piece 3: CLIP box predictor --- */
 /* loss modes */
 enum { CDDMSL_LOSS_FOCAL = 0, CDDMSL_LOSS_CE = 1, CDDMSL_LOSS_WEIGHTED_CE = 2 };

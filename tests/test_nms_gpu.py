@@ -147,3 +147,68 @@ def test_find_top_rpn_proposals_matches_oracle():
     bad[0, 3, 2] = float("inf")
     with pytest.raises(FloatingPointError):
         find_top_rpn_proposals([bad.to(DEV)], [logits.to(DEV)], [(600, 1000)] * n_img, 0.7, 4000, 1000, 0.0, True)
+
+
+@pytest.mark.parametrize("trick_limit", [4000, 100000])
+def test_batched_images_equals_per_image_calls(trick_limit):
+    """cddmsl_nms_batched (padded [B,M], counts on the device) is bit-identical, image by image, to cddmsl_nms on
+    that image's first counts[b] boxes -- ragged counts, an empty image, several classes, both class-handling modes."""
+    import importlib
+
+    lnms = importlib.import_module("cddmsl_b200.layers.nms")   # (`cddmsl_b200.layers.nms` the attribute is the function)
+    from cddmsl_b200.layers import batched_nms, batched_nms_images
+
+    g = synth.generator(33)
+    nb, m = 5, 700
+    counts = [700, 1, 0, 333, 64]
+    boxes = torch.stack([synth.make_boxes(m, 600, 1000, g) for _ in range(nb)])
+    boxes[1] += 3000.0            # a different max coordinate per image (coordinate-trick offset is per image)
+    scores = torch.randn(nb, m, generator=g).round(decimals=1)      # plenty of exact ties
+    idxs = torch.randint(0, 3, (nb, m), generator=g)
+    old = lnms.COORD_TRICK_NUMEL_LIMIT
+    lnms.COORD_TRICK_NUMEL_LIMIT = trick_limit
+    try:
+        keep, nk = batched_nms_images(boxes.to(DEV), scores.to(DEV), idxs.to(DEV),
+                                      torch.tensor(counts, dtype=torch.int32, device=DEV), 0.5)
+        nk = nk.tolist()
+        for b in range(nb):
+            c = counts[b]
+            # same mode as the batched call (rule evaluated on the padded size)
+            lnms.COORD_TRICK_NUMEL_LIMIT = 10 ** 9 if m * 4 <= trick_limit else 0
+            want = batched_nms(boxes[b, :c].to(DEV), scores[b, :c].to(DEV), idxs[b, :c].to(DEV), 0.5)
+            lnms.COORD_TRICK_NUMEL_LIMIT = trick_limit
+            assert nk[b] == want.numel()
+            assert torch.equal(keep[b, : nk[b]], want)
+    finally:
+        lnms.COORD_TRICK_NUMEL_LIMIT = old
+    # B = 1 with a device-side count, no class ids
+    keep, nk = batched_nms_images(boxes[:1].to(DEV), scores[:1].to(DEV), None,
+                                  torch.tensor([500], dtype=torch.int32, device=DEV), 0.5)
+    want = batched_nms(boxes[0, :500].to(DEV), scores[0, :500].to(DEV), torch.zeros(500, dtype=torch.int64, device=DEV), 0.5)
+    assert torch.equal(keep[0, : int(nk[0])], want)
+
+
+def test_find_top_rpn_proposals_batched_equals_loop():
+    """The all-images-at-once evaluation (one NMS call, one sync) returns exactly what the upstream-shaped loop does,
+    including non-finite boxes dropped at inference and the min_box_size filter."""
+    import cddmsl_b200.modeling.proposal_utils as pu
+
+    g = synth.generator(34)
+    n_img, a = 3, 3000
+    props = torch.stack([synth.make_boxes(a, 700, 1100, g, degenerate_frac=0.05) - 40.0 for _ in range(n_img)])
+    logits = torch.randn(n_img, a, generator=g)
+    props[1, 5, 1] = float("nan")
+    props[2, 9, 3] = float("inf")
+    logits[0, 17] = float("-inf")
+    sizes = [(600, 1000), (580, 990), (600, 800)]
+    args = ([props.to(DEV)], [logits.to(DEV)], sizes, 0.7, 2000, 500, 4.0, False)
+    batched = pu.find_top_rpn_proposals(*args)
+    pu.BATCHED_IMAGES = False
+    try:
+        loop = pu.find_top_rpn_proposals(*args)
+    finally:
+        pu.BATCHED_IMAGES = True
+    for rb, rl in zip(batched, loop):
+        assert torch.equal(rb.proposal_boxes.tensor, rl.proposal_boxes.tensor)
+        assert torch.equal(rb.objectness_logits, rl.objectness_logits)
+        assert len(rb.objectness_logits) > 0

@@ -119,6 +119,29 @@ def main():
                       "ours_boxes_per_s": m / (ours * 1e-3), "speedup": tv / ours,
                       "algorithmic_GBps": mask_bytes / (ours * 1e-3) / 1e9})
     res["nms"] = sweep
+
+    # ---- the RPN call site: 16 images x 12000 pre-NMS proposals (proposal_utils.py:42-66), one level
+    from cddmsl_b200.layers import batched_nms_images
+    nb, m = cfg.n_images, 12000
+    gg = synth.generator(777)
+    per = [synth.make_nms_inputs(m, cfg.img_h, cfg.img_w, gg, num_classes=1) for _ in range(nb)]
+    bb = torch.stack([p[0] for p in per]).to(dev)
+    ss = torch.stack([p[1] for p in per]).to(dev)
+    ii = torch.stack([p[2] for p in per]).to(dev)
+    cnt = torch.full((nb,), m, dtype=torch.int32, device=dev)
+
+    def ours_images():
+        keep, nk = batched_nms_images(bb, ss, ii, cnt, 0.7)
+        return nk.tolist()          # the one sync of the batch
+
+    def ours_loop():
+        return [batched_nms(bb[i], ss[i], ii[i], 0.7) for i in range(nb)]
+
+    def tv_loop():
+        return [tv_batched_nms(bb[i], ss[i], ii[i], 0.7) for i in range(nb)]
+
+    res["nms_rpn_batch"] = {"images": nb, "boxes_per_image": m, "ours_one_call_ms": timeit(ours_images, 5),
+                            "ours_per_image_loop_ms": timeit(ours_loop, 5), "torchvision_cuda_loop_ms": timeit(tv_loop, 3)}
     txt = json.dumps(res, indent=1)
     print(txt)
     if args.out:
