@@ -137,6 +137,33 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------- reference arm
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffers are allocated, so
+    the pages the copy engines read and write live on the GPU's own NUMA node (with N ranks streaming ~190 MB each
+    way per step, remote-node pinned memory caps the aggregate PCIe rate).  Best effort: returns the number of CPUs
+    bound, 0 when NVML / affinity is unavailable or the container's cpuset has no CPU on that node."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            try:
+                phys = int(vis.split(",")[index])
+            except Exception:
+                phys = index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(os.cpu_count() or 64, 64) + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        use = cpus & os.sched_getaffinity(0)
+        if use:
+            os.sched_setaffinity(0, use)
+        return len(use)
+    except Exception:
+        return 0
+
+
 def cpu_reference_step(cfg, sample_images: int, sample_rpi: int, seed: int):
     """One pass of the reference's CPU path on a bounded sample; returns (seconds, n_rois)."""
     from oracle import torch_ref
@@ -213,6 +240,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    numa_cpus = bind_to_gpu_numa_node(local) if (world > 1 and not os.environ.get("CDDMSL_NO_NUMA_BIND")) else 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -406,7 +434,8 @@ def run_ours(args):
         e2e = {"value": world * R * k2 / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms2 / k2, "steps": k2,
                "api": "ROIAlign.forward + FastRCNNOutputLayers.forward/losses + caption_consistency_loss + autograd",
-               "pipelining": "H2D(i+1) and D2H(i-1) on side streams overlap compute(i); all copies inside the timed region"}
+               "pipelining": "H2D(i+1) and D2H(i-1) on side streams overlap compute(i); all copies inside the timed region",
+               "numa_bound_cpus": numa_cpus}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:

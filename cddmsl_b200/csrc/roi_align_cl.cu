@@ -362,6 +362,36 @@ roi_align_fwd_cl_kernel(const float* __restrict__ ft, const float* __restrict__ 
   }
 }
 
+// ---- mbarrier + 1-D TMA bulk load (global -> shared), used to bring the contiguous grad tile in -----------------
+__device__ __forceinline__ uint32_t roi_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void roi_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(roi_smem_u32(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void roi_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(roi_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   roi_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(roi_smem_u32(bar))
+               : "memory");
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void roi_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = roi_smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -542,6 +572,22 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
     }
     return;
   }
+  // The grad tile of a channel group is one contiguous [GC][PER] block: a single TMA bulk load per group, issued
+  // BEFORE the tap tables are built so the copy engine works under the prologue (was: LDG -> STS by every thread,
+  // 17 % of the kernel's stall samples sat on those STS).
+  __shared__ __align__(8) uint64_t tile_bar;
+  if (threadIdx.x == 0) roi_mbar_init(&tile_bar);
+  __syncthreads();
+  uint32_t tile_phase = 0;
+  auto tile_is_bulk = [&](int c0) {
+    const int nc = min(GC, cend - c0);
+    return ((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(gout + ((size_t)r * C + c0) * PER) & 15) == 0);
+  };
+  auto issue_tile = [&](int c0) {
+    if (threadIdx.x == 0 && tile_is_bulk(c0))
+      roi_bulk_load(G_s, gout + ((size_t)r * C + c0) * PER, (uint32_t)(min(GC, cend - c0) * PER) * 4u, &tile_bar);
+  };
+  issue_tile(cbeg);
   build_tables<P, NT>(xtab, nullptr, g, H, W);
   for (int t = threadIdx.x; t < NW * g.gh; t += NT) {  // merged row slots of every (row pair, sample)
     const int j = t / g.gh, i = t - j * g.gh;
@@ -555,12 +601,10 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
     const int nc = min(GC, cend - c0);
     const float* g_tile = gout + ((size_t)r * C + c0) * PER;
     float* img = gt + (size_t)g.batch * H * W * C + c0;
-    // stage the contiguous grad tile (read once, streaming)
-    if (((nc * PER) % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_tile) & 15) == 0)) {
-      const float4* s4 = reinterpret_cast<const float4*>(g_tile);
-      float4* d4 = reinterpret_cast<float4*>(G_s);
-      for (int e = threadIdx.x; e < nc * PER / 4; e += NT) d4[e] = __ldcs(s4 + e);
-    } else {
+    if (tile_is_bulk(c0)) {
+      roi_mbar_wait(&tile_bar, tile_phase);
+      tile_phase ^= 1u;
+    } else {  // unaligned / ragged tile (7x7 with an odd channel offset): plain loads
       for (int e = threadIdx.x; e < nc * PER; e += NT) G_s[e] = __ldcs(g_tile + e);
     }
     __syncthreads();  // tile (and, the first time round, the tables) visible
@@ -573,7 +617,10 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
       else
         bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
     }
-    if (c0 + GC < cend) __syncthreads();  // next group overwrites the tile
+    if (c0 + GC < cend) {
+      __syncthreads();  // every warp is done reading the tile: the next group's copy may overwrite it
+      issue_tile(c0 + GC);
+    }
   }
 }
 
