@@ -65,3 +65,7 @@ def test_workspace_queries_do_not_need_a_gpu():
     assert L.cddmsl_nms_workspace_bytes(12000) > 12000 * 188 * 8
     assert L.cddmsl_align_loss_workspace_bytes(8, 256, 256) >= 2048 * 2048 * 4
     assert L.cddmsl_roi_align_bwd_workspace_bytes(16, 1024, 38, 63, 8192) > 0
+    # batched NMS: B images' masks; a single image through the batched entry point sizes for the segmented sort
+    assert L.cddmsl_nms_batched_workspace_bytes(16, 12000) > 16 * 12000 * 188 * 8
+    assert L.cddmsl_nms_batched_workspace_bytes(1, 12000) >= L.cddmsl_nms_workspace_bytes(12000)
+    assert L.cddmsl_box_reg_loss_workspace_bytes(8192) >= 32 * 4
