@@ -28,6 +28,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace cddmsl {
 
@@ -464,34 +465,12 @@ __global__ void clip_head_tc_transpose_w_kernel(const float* __restrict__ wall, 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 // row-major fp32 [rows, cols] (ld floats between rows), box [TC_BK cols x 128 rows], 128-byte swizzle
 static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return CDDMSL_EINVAL;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : CDDMSL_EINVAL;
+  return tma_encode_2d_f32(m, base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld * 4,
+                           TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)
+             ? CDDMSL_EINVAL
+             : 0;
 }
 
 static int launch_gemm(const float* A, int M, int lda, const float* B, int N, int ldb, int K, TcEpilogue ep,

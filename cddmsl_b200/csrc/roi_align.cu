@@ -411,7 +411,7 @@ static int g_fwd_cc = 32;
 static int g_bwd_smem_kb = 56;
 static int g_bwd_cc = 32;
 static int g_use_cl = 1;
-extern int g_fwd_cpl, g_bwd_cpl, g_roi_gpc;  // channels-last fast path (roi_align_cl.cu) for the 14x14 pooler
+extern int g_fwd_cpl, g_bwd_cpl, g_roi_gpc, g_roi_tma;  // channels-last fast path (roi_align_cl.cu) for the 14x14 pooler
 
 bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW);
 size_t roi_cl_workspace_bytes(int N, int C, int H, int W);
@@ -429,6 +429,7 @@ int tune_roi(const char* key, int value) {
   else if (!strcmp(key, "roi_fwd_cpl")) g_fwd_cpl = value;
   else if (!strcmp(key, "roi_bwd_cpl")) g_bwd_cpl = value;
   else if (!strcmp(key, "roi_gpc")) g_roi_gpc = value;
+  else if (!strcmp(key, "roi_tma")) g_roi_tma = value;
   else return 0;
   return 1;
 }

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "roi_common.cuh"
+#include "tma_host.cuh"
 
 namespace cddmsl {
 
@@ -230,7 +231,8 @@ template <int P, int GH, int CPL>
 __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image + first channel of this lane */,
                                          const TapE* __restrict__ xtab, const TapE* __restrict__ ytab, int gw, int gh,
                                          int W, int C, int row_a, float* __restrict__ orow /* tile row of channel lane */,
-                                         int nch /* channels of this lane that exist */) {
+                                         int nch /* channels of this lane that exist */,
+                                         int kstride = 32 * P * P /* floats between channels l and l+32 in the tile */) {
   const int WC = W * C;
   const unsigned Cb = (unsigned)C * 4u;  // bytes between two columns of the channels-last map
   RowTaps<GH> ra, rb;
@@ -259,7 +261,7 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       if (k < nch) {
-        float* o = orow + k * 32 * P * P;
+        float* o = orow + k * kstride;
         if (P % 2 == 0) {
           *reinterpret_cast<float2*>(o + pw) = make_float2(sa0.v[k], sa1.v[k]);
           *reinterpret_cast<float2*>(o + P + pw) = make_float2(sb0.v[k], sb1.v[k]);
@@ -496,7 +498,8 @@ __device__ __forceinline__ void bwd_flush(float* __restrict__ base, unsigned xb,
 template <int P, bool GH1, int CPL>
 __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* __restrict__ xtab,
                                          const YSlots* __restrict__ slots, int gw, int gh, int W, int C,
-                                         const float* __restrict__ grow, int nch, bool row_b_exists) {
+                                         const float* __restrict__ grow, int nch, bool row_b_exists,
+                                         int kstride = 32 * P * P) {
   YSlots s1;
   if (GH1) s1 = slots[0];
   const unsigned Cb = (unsigned)C * 4u;
@@ -508,7 +511,7 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
     float2 ga[CPL], gb[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
-      const float* gq = grow + (q < nch ? q : 0) * 32 * P * P;
+      const float* gq = grow + (q < nch ? q : 0) * kstride;
       if (P % 2 == 0) {
         ga[q] = *reinterpret_cast<const float2*>(gq + pw);
         gb[q] = *reinterpret_cast<const float2*>(gq + P + pw);
@@ -625,6 +628,151 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// 14x14, C % 64 == 0: warps decoupled through per-warp TMA tensor copies
+// ------------------------------------------------------------------------------------------------
+// The kernels above move the [64][196] tile of a channel group with ONE bulk copy, so every group costs CTA-wide
+// barriers (ncu: barrier = 14 % of the forward's stall cycles, the mbarrier spin 12 % of the backward's samples).
+// Warp j only ever touches rows 2j, 2j+1 of the 64 channels: a [64 channels][28 floats] box of the [R*C][196] view
+// of the pooled tensor.  That box is exactly what a 2-D TMA tensor copy moves, so here each warp owns a private
+// [64][28] staging buffer (same 49 KB per CTA in total) and issues its own cp.async.bulk.tensor: no barrier after
+// the tap tables are built, warps drift freely through the channel groups.
+constexpr int kRowsPerWarp = 2;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(roi_smem_u32(smem_src)), "r"(x), "r"(y)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_warp(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar,
+                                                 uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(roi_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          roi_smem_u32(smem_dst)),
+      "l"(map), "r"(roi_smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(7 * 32, 4)
+roi_align_fwd_cl_tma_kernel(const float* __restrict__ ft, const float* __restrict__ in_nchw,
+                            const float* __restrict__ rois, float* __restrict__ out,
+                            const __grid_constant__ CUtensorMap out_map, int N, int C, int H, int W, int R, float scale,
+                            int sampling_ratio, int aligned, int ngroups, int gpc) {
+  constexpr int P = 14, NW = 7, NT = NW * 32, PER = P * P, GC = 32 * CPL, PE = 14, WROW = kRowsPerWarp * P;
+  extern __shared__ __align__(128) float dyn_smem[];
+  float* stage = dyn_smem;                                       // [NW][GC][WROW]
+  TapE* xtab = reinterpret_cast<TapE*>(stage + NW * GC * WROW);  // [PE * kMaxG]
+  TapE* ytab = xtab + PE * kMaxG;
+  const int r = blockIdx.x / ngroups;
+  const int cbeg = (blockIdx.x - r * ngroups) * (GC * gpc);
+  const int cend = min(C, cbeg + GC * gpc);
+  const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
+  if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) {
+    float* o = out + ((size_t)r * C + cbeg) * PER;
+    for (int e = threadIdx.x; e < (cend - cbeg) * PER; e += NT) o[e] = 0.f;
+    return;
+  }
+  if (g.gw > kMaxG || g.gh > kMaxG) {
+    fwd_direct_any(in_nchw, out + (size_t)r * C * PER, cbeg, cend - cbeg, C, H, W, P, P, g, NT);
+    return;
+  }
+  build_tables<P, NT>(xtab, ytab, g, H, W);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* wst = stage + warp * (GC * WROW);
+  float* orow = wst + lane * WROW;
+  bool pending = false;
+  for (int c0 = cbeg; c0 < cend; c0 += GC) {  // C % GC == 0: every group is full
+    const float* base = ft + (size_t)g.batch * H * W * C + c0 + lane;
+    if (pending) {  // the copy engine must have read this warp's previous box before it is overwritten
+      // (deferring this wait behind the first bins' loads was measured: no gain)
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+    if (g.gh == 1) fwd_rows<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
+    else if (g.gh == 2) fwd_rows<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
+    else fwd_rows<P, 0, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) tma_store_2d(&out_map, wst, WROW * warp, r * C + c0);
+    pending = true;
+  }
+  if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the read
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(7 * 32, 4)
+roi_align_bwd_cl_tma_kernel(const __grid_constant__ CUtensorMap gout_map, const float* __restrict__ gout,
+                            const float* __restrict__ rois, float* __restrict__ gt, int N, int C, int H, int W, int R,
+                            float scale, int sampling_ratio, int aligned, int ngroups, int gpc) {
+  constexpr int P = 14, NW = 7, NT = NW * 32, PER = P * P, GC = 32 * CPL, PE = 14, WROW = kRowsPerWarp * P;
+  extern __shared__ __align__(128) float dyn_smem[];
+  float* stage = dyn_smem;                                          // [NW][GC][WROW]
+  TapE* xtab = reinterpret_cast<TapE*>(stage + NW * GC * WROW);     // [PE * kMaxG]
+  YSlots* yslots = reinterpret_cast<YSlots*>(xtab + PE * kMaxG);    // [NW][kMaxG]
+  __shared__ __align__(8) uint64_t bars[NW];
+  const int r = blockIdx.x / ngroups;
+  const int cbeg = (blockIdx.x - r * ngroups) * (GC * gpc);
+  const int cend = min(C, cbeg + GC * gpc);
+  const RoiGeom g = roi_geom(rois + (size_t)r * 5, scale, aligned, P, P, sampling_ratio, H, W);
+  if (g.gw <= 0 || g.gh <= 0 || g.batch < 0 || g.batch >= N) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g.gw > kMaxG || g.gh > kMaxG) {  // reference-style scatter into the channels-last map
+    const float* g_tile = gout + ((size_t)r * C + cbeg) * PER;
+    float* img = gt + (size_t)g.batch * H * W * C + cbeg;
+    for (int e = threadIdx.x; e < (cend - cbeg) * PER; e += NT) {
+      const int c = e / PER, b = e - c * PER;
+      const int ph = b / P, pw = b - ph * P;
+      const float go = g_tile[e] * g.inv_count;
+      for (int iy = 0; iy < g.gh; ++iy) {
+        const Tap ty = make_tap(g.sh, g.bh, ph, iy, g.gh, H, 0);
+        if (ty.wl == 0.f && ty.wh == 0.f) continue;
+        for (int ix = 0; ix < g.gw; ++ix) {
+          const Tap tx = make_tap(g.sw, g.bw, pw, ix, g.gw, W, 0);
+          if (tx.wl == 0.f && tx.wh == 0.f) continue;
+          red_add(img + ((size_t)ty.lo * W + tx.lo) * C + c, go * ty.wl * tx.wl);
+          red_add(img + ((size_t)ty.lo * W + tx.hi) * C + c, go * ty.wl * tx.wh);
+          red_add(img + ((size_t)ty.hi * W + tx.lo) * C + c, go * ty.wh * tx.wl);
+          red_add(img + ((size_t)ty.hi * W + tx.hi) * C + c, go * ty.wh * tx.wh);
+        }
+      }
+    }
+    return;
+  }
+  float* wst = stage + warp * (GC * WROW);
+  uint64_t* bar = &bars[warp];
+  constexpr uint32_t kBoxBytes = GC * WROW * 4;
+  if (lane == 0) {  // this warp's first box flies while the tables are built
+    roi_mbar_init(bar);
+    tma_load_2d_warp(wst, &gout_map, WROW * warp, r * C + cbeg, bar, kBoxBytes);
+  }
+  build_tables<P, NT>(xtab, nullptr, g, H, W);
+  for (int t = threadIdx.x; t < NW * g.gh; t += NT) {
+    const int j = t / g.gh, i = t - j * g.gh;
+    yslots[j * kMaxG + i] = make_slots(make_tap_entry(g.sh, g.bh, 2 * j, i, g.gh, H, 1.f),
+                                       make_tap_entry(g.sh, g.bh, 2 * j + 1, i, g.gh, H, 1.f), W * C);
+  }
+  __syncthreads();  // tables (and every warp's mbarrier init) visible
+  uint32_t phase = 0;
+  const float* grow = wst + lane * WROW;
+  for (int c0 = cbeg; c0 < cend; c0 += GC) {
+    float* img = gt + (size_t)g.batch * H * W * C + c0;
+    roi_mbar_wait(bar, phase);
+    phase ^= 1u;
+    if (g.gh == 1)
+      bwd_rows<P, true, CPL>(img + lane, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, CPL, true, 32 * WROW);
+    else
+      bwd_rows<P, false, CPL>(img + lane, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, CPL, true, 32 * WROW);
+    if (c0 + GC < cend) {
+      __syncwarp();  // every lane is done reading the box
+      if (lane == 0) tma_load_2d_warp(wst, &gout_map, WROW * warp, r * C + c0 + GC, bar, kBoxBytes);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW) {
@@ -671,10 +819,61 @@ static int launch_bwd_cl(const float* gout, const float* rois, float* gt, int N,
   return (int)cudaGetLastError();
 }
 
+// tuning knob "roi_tma": per-warp TMA tensor copies for 14x14 when C % 64 == 0; bit 0 = forward, bit 1 = backward.
+// Measured (cfg #2): forward 2.66 -> 2.52 ms; backward 2.57 -> 3.33 ms (sixty-four 112-byte row fetches per box cost
+// more than the barrier they remove) -- so the default enables the forward only.
+int g_roi_tma = 1;
+
+static bool roi_tma_ok(int C, int R, int P, int bit) {
+  return (g_roi_tma & bit) && P == 14 && C % 64 == 0 && (long long)R * C < 0x7fffffffLL;
+}
+
+static int launch_fwd_cl_tma(const float* ft, const float* in, const float* rois, float* out, int N, int C, int H,
+                             int W, int R, float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
+  constexpr int CPL = 2, P = 14;
+  CUtensorMap map;
+  if (tma_encode_2d_f32(&map, out, P * P, (unsigned long long)R * C, P * P * 4, kRowsPerWarp * P, 32 * CPL,
+                        CU_TENSOR_MAP_SWIZZLE_NONE))
+    return CDDMSL_EINVAL;
+  const int gpc = max(1, g_roi_gpc);
+  const int ngroups = ceil_div(C, 32 * CPL * gpc);
+  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
+  const int smem = 32 * CPL * P * P * 4 + 2 * P * kMaxG * (int)sizeof(TapE);
+  auto k = roi_align_fwd_cl_tma_kernel<CPL>;
+  cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ea != cudaSuccess) return (int)ea;
+  k<<<(unsigned)((long long)R * ngroups), 7 * 32, smem, stream>>>(ft, in, rois, out, map, N, C, H, W, R, scale,
+                                                                 sampling_ratio, aligned, ngroups, gpc);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+static int launch_bwd_cl_tma(const float* gout, const float* rois, float* gt, int N, int C, int H, int W, int R,
+                             float scale, int sampling_ratio, int aligned, cudaStream_t stream) {
+  constexpr int CPL = 2, P = 14;
+  CUtensorMap map;
+  if (tma_encode_2d_f32(&map, gout, P * P, (unsigned long long)R * C, P * P * 4, kRowsPerWarp * P, 32 * CPL,
+                        CU_TENSOR_MAP_SWIZZLE_NONE))
+    return CDDMSL_EINVAL;
+  const int gpc = max(1, g_roi_gpc);
+  const int ngroups = ceil_div(C, 32 * CPL * gpc);
+  if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
+  const int smem = 32 * CPL * P * P * 4 + P * kMaxG * (int)sizeof(TapE) + 7 * kMaxG * (int)sizeof(YSlots);
+  auto k = roi_align_bwd_cl_tma_kernel<CPL>;
+  cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ea != cudaSuccess) return (int)ea;
+  k<<<(unsigned)((long long)R * ngroups), 7 * 32, smem, stream>>>(map, gout, rois, gt, N, C, H, W, R, scale,
+                                                                 sampling_ratio, aligned, ngroups, gpc);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, int P,
                      float scale, int sampling_ratio, int aligned, float* ft, cudaStream_t stream) {
   int rc = launch_transpose(in, ft, N, C, H * W, stream);  // NCHW -> NHWC
   if (rc) return rc;
+  if (R > 0 && roi_tma_ok(C, R, P, 1) && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    return launch_fwd_cl_tma(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
   if (P == 7) return launch_fwd_cl<7, 2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
   return g_fwd_cpl == 2 ? launch_fwd_cl<14, 2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
                         : launch_fwd_cl<14, 1>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
@@ -684,7 +883,9 @@ int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, in
                      float scale, int sampling_ratio, int aligned, float* gt, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(gt, 0, (size_t)N * C * H * W * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
-  int rc = P == 7 ? launch_bwd_cl<7, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+  int rc = (R > 0 && roi_tma_ok(C, R, P, 2) && (reinterpret_cast<uintptr_t>(gout) & 15) == 0)
+               ? launch_bwd_cl_tma(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+           : P == 7 ? launch_bwd_cl<7, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
            : g_bwd_cpl == 2
                ? launch_bwd_cl<14, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
                : launch_bwd_cl<14, 1>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
