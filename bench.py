@@ -468,7 +468,7 @@ def run_ours(args):
     traffic = None
     try:  # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["kernels"]
-        key = "roi_align_bwd_cl_kernel" if dom == "roi_align_bwd" else "roi_align_fwd_cl_kernel"
+        key = "roi_align_bwd_cl" if dom == "roi_align_bwd" else "roi_align_fwd_cl"
         traffic = next(v["dram_bytes"] for k, v in tj.items() if k.startswith(key)) if args.workload == "voc" else None
     except Exception:
         traffic = None
