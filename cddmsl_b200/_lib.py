@@ -38,6 +38,8 @@ SIGNATURES = {
                                    _vp, _sz, _vp]),
     "cddmsl_box_reg_loss_workspace_bytes": (_sz, [_i]),
     "cddmsl_box_reg_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cddmsl_match_boxes_workspace_bytes": (_sz, [_i, _i]),
+    "cddmsl_match_boxes": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cddmsl_align_pack_normalized": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "cddmsl_align_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "cddmsl_align_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

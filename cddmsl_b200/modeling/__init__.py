@@ -3,9 +3,13 @@ from .box_regression import Box2BoxTransform
 from .caption_consistency import caption_consistency_loss, image_caption_consistency_loss
 from .fast_rcnn import FastRCNNOutputLayers, fast_rcnn_inference, fast_rcnn_inference_single_image
 from .gather import GatherLayer
+from .matcher import Matcher, pairwise_iou
 from .poolers import ROIPooler, convert_boxes_to_pooler_format
 from .proposal_utils import find_top_rpn_proposals
+from .roi_heads import ROIHeads, add_ground_truth_to_proposals
+from .sampling import subsample_labels
 
 __all__ = ["Box2BoxTransform", "caption_consistency_loss", "image_caption_consistency_loss",
            "FastRCNNOutputLayers", "fast_rcnn_inference", "fast_rcnn_inference_single_image", "GatherLayer",
-           "ROIPooler", "convert_boxes_to_pooler_format", "find_top_rpn_proposals"]
+           "ROIPooler", "convert_boxes_to_pooler_format", "find_top_rpn_proposals", "Matcher", "pairwise_iou", "ROIHeads",
+           "add_ground_truth_to_proposals", "subsample_labels"]

@@ -152,6 +152,49 @@ def _(boxes, scores, idxs, counts, iou_threshold, coord_trick):
     return scores.new_empty(scores.shape, dtype=torch.int64), scores.new_empty((scores.shape[0],), dtype=torch.int32)
 
 
+# ------------------------------------------------------------------------------------ proposal matching
+@torch.library.custom_op("cddmsl_b200::match_boxes", mutates_args=(), device_types="cuda")
+def match_boxes(gt_boxes: Tensor, gt_counts: Tensor, boxes: Tensor, counts: Optional[Tensor],
+                thresholds: List[float], labels: List[int], allow_low_quality_matches: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """pairwise IoU + Matcher for B images at once (boxes.py:346-368, matcher.py:63-127), no IoU matrix.
+    gt_boxes [B,G,4], gt_counts int32 [B], boxes [B,M,4], counts int32 [B] or None.
+    Returns (matches int64 [B,M], match_labels int8 [B,M], matched_vals float [B,M])."""
+    import ctypes
+
+    _lib.require_cuda(boxes, "boxes")
+    bx, gb = _f32c(boxes), _f32c(gt_boxes)
+    nb, m = bx.shape[0], bx.shape[1]
+    g = gb.shape[1]
+    assert bx.shape == (nb, m, 4) and gb.shape == (nb, g, 4) and gt_counts.numel() == nb
+    dev = bx.device
+    matches = torch.zeros((nb, m), dtype=torch.int64, device=dev)
+    mlabels = torch.zeros((nb, m), dtype=torch.int8, device=dev)
+    mvals = torch.zeros((nb, m), dtype=torch.float32, device=dev)
+    if nb == 0 or m == 0:
+        return matches, mlabels, mvals
+    gc = gt_counts.to(device=dev, dtype=torch.int32).contiguous()
+    cnt = None if counts is None else counts.to(device=dev, dtype=torch.int32).contiguous()
+    thr = (ctypes.c_float * len(thresholds))(*[float(t) for t in thresholds])
+    lab = (ctypes.c_int32 * len(labels))(*[int(v) for v in labels])
+    assert len(labels) == len(thresholds) + 1
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_match_boxes_workspace_bytes(nb, g), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.cddmsl_match_boxes(_lib.ptr(gb) if g > 0 else None, _lib.ptr(gc), _lib.ptr(bx), _lib.ptr(cnt), nb,
+                                        g, m, ctypes.cast(thr, ctypes.c_void_p), ctypes.cast(lab, ctypes.c_void_p),
+                                        len(thresholds), int(allow_low_quality_matches), _lib.ptr(matches),
+                                        _lib.ptr(mlabels), _lib.ptr(mvals), _lib.ptr(ws), ws.numel(),
+                                        _lib.stream_ptr(dev)), "match_boxes")
+    return matches, mlabels, mvals
+
+
+@match_boxes.register_fake
+def _(gt_boxes, gt_counts, boxes, counts, thresholds, labels, allow_low_quality_matches):
+    nb, m = boxes.shape[0], boxes.shape[1]
+    return (boxes.new_empty((nb, m), dtype=torch.int64), boxes.new_empty((nb, m), dtype=torch.int8),
+            boxes.new_empty((nb, m), dtype=torch.float32))
+
+
 # ------------------------------------------------------------------------------------------ CLIP head
 def _head_ws(r, d, k, device):
     return _ws(_lib.lib().cddmsl_clip_head_workspace_bytes(r, d, k), device)

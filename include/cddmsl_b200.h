@@ -118,6 +118,21 @@ int cddmsl_box_reg_loss(const float* proposal_boxes, const float* gt_boxes, cons
                         float wh, float beta, const float* grad_scale, float* loss, float* dpred, void* workspace,
                         size_t workspace_bytes, cddmsl_stream_t stream);
 
+/* ---------------------------------------------------------------- next row: proposal matching -- */
+/* pairwise_iou (detectron2/structures/boxes.py:346-368) + Matcher.__call__ / set_low_quality_matches_
+ * (detectron2/modeling/matcher.py:63-127) for the B images of a batch in one pass, as label_and_sample_proposals
+ * (roi_heads.py:285-289) and the RPN's anchor labelling use them; the [G, M] IoU matrix is never materialised.
+ * Padded layout: gt_boxes [B][Gmax][4] with gt_counts int32[B] on the device, boxes [B][Mmax][4] with counts int32[B]
+ * on the device (nullable: every image holds Mmax boxes).  thresholds (host, ascending, first > 0) and labels (host,
+ * num_thresholds + 1 values in {-1,0,1}) are the Matcher's constructor arguments.  Outputs per candidate: matches
+ * int64 (argmax gt, first maximum; 0 when the image has no gt), match_labels int8, matched_vals float (nullable).
+ * Bit-identical to the reference arithmetic (unfused fp32 IoU).  workspace: only with allow_low_quality_matches. */
+size_t cddmsl_match_boxes_workspace_bytes(int B, int Gmax);
+int cddmsl_match_boxes(const float* gt_boxes, const int32_t* gt_counts, const float* boxes, const int32_t* counts,
+                       int B, int Gmax, int Mmax, const float* thresholds, const int32_t* labels, int num_thresholds,
+                       int allow_low_quality_matches, int64_t* matches, int8_t* match_labels, float* matched_vals,
+                       void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+
 /* ---------------------------------------------------------------- piece 4: alignment loss ------- */
 /* Row-normalise src|tgt [n_local,D] each (x / |x|, no eps — rcnn.py:308-309, :458-459) and pack them as
  * packed[2][n_local][D] for ONE all-gather per branch (the reference issues two, rcnn.py:455-456;

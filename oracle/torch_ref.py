@@ -228,3 +228,41 @@ def box_reg_loss(proposal_boxes, gt_boxes, pred_deltas, gt_classes, num_classes:
         fg_pred = pred_deltas.view(-1, num_classes, 4)[fg, gt_classes[fg]]
     tgt = get_deltas(proposal_boxes[fg], gt_boxes[fg], weights)
     return smooth_l1_sum(fg_pred, tgt, beta) / max(gt_classes.numel(), 1.0)
+
+
+def pairwise_iou(boxes1: torch.Tensor, boxes2: torch.Tensor) -> torch.Tensor:
+    """detectron2/structures/boxes.py:320-368 (pairwise_intersection + pairwise_iou) on [N,4] / [M,4] tensors."""
+    area1 = (boxes1[:, 2] - boxes1[:, 0]) * (boxes1[:, 3] - boxes1[:, 1])
+    area2 = (boxes2[:, 2] - boxes2[:, 0]) * (boxes2[:, 3] - boxes2[:, 1])
+    wh = torch.min(boxes1[:, None, 2:], boxes2[:, 2:]) - torch.max(boxes1[:, None, :2], boxes2[:, :2])
+    wh.clamp_(min=0)
+    inter = wh.prod(dim=2)
+    return torch.where(inter > 0, inter / (area1[:, None] + area2 - inter), torch.zeros(1, dtype=inter.dtype))
+
+
+def matcher(match_quality_matrix: torch.Tensor, thresholds, labels, allow_low_quality_matches: bool = False):
+    """detectron2/modeling/matcher.py:63-127 (Matcher.__call__ + set_low_quality_matches_)."""
+    if match_quality_matrix.numel() == 0:
+        n = match_quality_matrix.size(1)
+        return torch.zeros(n, dtype=torch.int64), torch.full((n,), labels[0], dtype=torch.int8)
+    assert torch.all(match_quality_matrix >= 0)
+    bounds = [-float("inf")] + list(thresholds) + [float("inf")]
+    matched_vals, matches = match_quality_matrix.max(dim=0)
+    match_labels = torch.full(matches.size(), 1, dtype=torch.int8)
+    for l, low, high in zip(labels, bounds[:-1], bounds[1:]):
+        match_labels[(matched_vals >= low) & (matched_vals < high)] = l
+    if allow_low_quality_matches:
+        highest, _ = match_quality_matrix.max(dim=1)
+        pred = (match_quality_matrix == highest[:, None]).nonzero()[:, 1]
+        match_labels[pred] = 1
+    return matches, match_labels
+
+
+def assign_classes(matched_idxs, matched_labels, gt_classes, num_classes: int):
+    """roi_heads.py:216-224: class of the matched gt; background for label 0, ignore for -1; no gt -> background."""
+    if gt_classes.numel() > 0:
+        out = gt_classes[matched_idxs].clone()
+        out[matched_labels == 0] = num_classes
+        out[matched_labels == -1] = -1
+        return out
+    return torch.zeros_like(matched_idxs) + num_classes

@@ -17,6 +17,10 @@ What it records (all seeded, fp32 / int64):
   * box_reg.npz — `Box2BoxTransform.get_deltas` of the reference (`detectron2/modeling/box_regression.py`, loaded
     verbatim with its unused imports stubbed) + fvcore's published smooth-L1 (fvcore is not vendored).
 
+  * match.npz — the reference's own `Matcher` (`detectron2/modeling/matcher.py`) on its own `pairwise_iou`
+    (`detectron2/structures/boxes.py`), both loaded verbatim with two import stubs: ROI-head and RPN settings,
+    an image without ground truth, duplicate gt boxes (argmax ties), degenerate proposals.
+
 The tests never read /root/reference; they read these files.
 """
 import importlib.util
@@ -241,15 +245,68 @@ def box_reg_cases():
     print("box_reg: agnostic perclass l1")
 
 
+def _load_with_stubs(name, rel, stubs):
+    import types
+
+    added = {}
+    for mod_name, attrs in stubs.items():
+        if mod_name not in sys.modules:
+            m = types.ModuleType(mod_name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[mod_name] = m
+            added[mod_name] = m
+    try:
+        return load_by_path(name, rel)
+    finally:
+        for mod_name in added:
+            sys.modules.pop(mod_name, None)
+
+
+def match_cases():
+    """Matcher + pairwise_iou come from the reference's own files (detectron2/modeling/matcher.py and
+    detectron2/structures/boxes.py, loaded verbatim; `detectron2.layers.nonzero_tuple` and
+    `detectron2.utils.env.TORCH_VERSION` stubbed)."""
+    def nonzero_tuple(x):
+        return x.nonzero().unbind(1) if x.dim() else x.unsqueeze(0).nonzero().unbind(1)
+
+    stubs = {"detectron2": {}, "detectron2.layers": {"nonzero_tuple": nonzero_tuple, "cat": torch.cat},
+             "detectron2.utils": {}, "detectron2.utils.env": {"TORCH_VERSION": (2, 0)}}
+    ref_m = _load_with_stubs("ref_matcher", "detectron2/modeling/matcher.py", stubs)
+    ref_b = _load_with_stubs("ref_boxes", "detectron2/structures/boxes.py", stubs)
+    g = synth.generator(16)
+    out = {}
+    g_len, m_len = [7, 0, 3, 40], [300, 200, 257, 1000]
+    for b, (ng, nm) in enumerate(zip(g_len, m_len)):
+        gt = synth.make_boxes(ng, 600, 1000, g, min_side=32.0, degenerate_frac=0.0) if ng else torch.zeros(0, 4)
+        if ng >= 3:
+            gt[2] = gt[0]                                   # duplicate gt: argmax tie -> first index
+        props = synth.make_boxes(nm, 600, 1000, g, degenerate_frac=0.03)
+        if ng:
+            jit = gt[torch.randint(0, ng, (nm // 3,), generator=g)] + torch.randn(nm // 3, 4, generator=g) * 6.0
+            props[: nm // 3] = jit                          # a third of the proposals hug a gt box
+            props = torch.cat([props, gt])                  # proposal_append_gt
+        out[f"gt_{b}"], out[f"boxes_{b}"] = gt.numpy(), props.numpy()
+        mqm = ref_b.pairwise_iou(ref_b.Boxes(gt), ref_b.Boxes(props))
+        out[f"iou_max_{b}"] = (mqm.max(dim=0).values if ng else torch.zeros(len(props))).numpy()
+        for tag, (thr, lab, low) in {"roi": ([0.5], [0, 1], False), "rpn": ([0.3, 0.7], [0, -1, 1], True)}.items():
+            matches, labels = ref_m.Matcher(thr, lab, allow_low_quality_matches=low)(mqm)
+            out[f"matches_{tag}_{b}"], out[f"labels_{tag}_{b}"] = matches.numpy(), labels.numpy()
+    out["n_images"] = np.array([len(g_len)])
+    np.savez_compressed(os.path.join(HERE, "match.npz"), **out)
+    print("match:", g_len, m_len)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
-    if len(sys.argv) > 1 and sys.argv[1] == "box_reg":
-        box_reg_cases()
+    if len(sys.argv) > 1 and sys.argv[1] in ("box_reg", "match"):
+        {"box_reg": box_reg_cases, "match": match_cases}[sys.argv[1]]()
         sys.exit(0)
     roi_cases()
     nms_cases()
     head_cases()
     align_cases()
     box_reg_cases()
+    match_cases()
     sizes = {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")}
     print(sizes, sum(sizes.values()))

@@ -191,3 +191,24 @@ def test_box_reg_oracle_matches_reference_get_deltas_fixture(golden_dir):
     bad[fg[0]] = torch.tensor([3.0, 3.0, 3.0, 9.0])
     with pytest.raises(AssertionError):
         torch_ref.box_reg_loss(bad, gtb, torch.zeros(len(gt), 4), gt, k, w, 0.5)
+
+
+MATCH_CFG = {"roi": ([0.5], [0, 1], False), "rpn": ([0.3, 0.7], [0, -1, 1], True)}
+
+
+def test_matcher_oracle_and_host_mirror_match_reference_fixture(golden_dir):
+    """match.npz comes from the reference's own Matcher + pairwise_iou (matcher.py, boxes.py loaded verbatim)."""
+    from cddmsl_b200.modeling import matcher as host
+
+    f = np.load(os.path.join(golden_dir, "match.npz"))
+    for b in range(int(f["n_images"][0])):
+        gt, boxes = torch.from_numpy(f[f"gt_{b}"]), torch.from_numpy(f[f"boxes_{b}"])
+        mqm = torch_ref.pairwise_iou(gt, boxes)
+        assert torch.equal(mqm, host.pairwise_iou(gt, boxes))
+        if len(gt):
+            assert np.array_equal(mqm.max(dim=0).values.numpy(), f[f"iou_max_{b}"])
+        for tag, (thr, lab, low) in MATCH_CFG.items():
+            for fn in (lambda q: torch_ref.matcher(q, thr, lab, low), host.Matcher(thr, lab, low)):
+                m, l = fn(mqm)
+                assert np.array_equal(m.numpy(), f[f"matches_{tag}_{b}"]), (tag, b)
+                assert np.array_equal(l.numpy(), f[f"labels_{tag}_{b}"]), (tag, b)

@@ -142,6 +142,32 @@ def main():
 
     res["nms_rpn_batch"] = {"images": nb, "boxes_per_image": m, "ours_one_call_ms": timeit(ours_images, 5),
                             "ours_per_image_loop_ms": timeit(ours_loop, 5), "torchvision_cuda_loop_ms": timeit(tv_loop, 3)}
+    # ---- proposal labelling / sampling before ROIAlign (roi_heads.py:236-319): 16 images x 2000 proposals, 8 gt each
+    import cddmsl_b200.modeling.roi_heads as rh
+    from cddmsl_b200.structures import Boxes, Instances
+    gg = synth.generator(778)
+    props, tgts = [], []
+    for _ in range(cfg.n_images):
+        t = Instances((cfg.img_h, cfg.img_w))
+        t.gt_boxes = Boxes(synth.make_boxes(8, cfg.img_h, cfg.img_w, gg, min_side=48.0, degenerate_frac=0.0).to(dev))
+        t.gt_classes = torch.randint(0, cfg.num_classes, (8,), generator=gg).to(dev)
+        p = Instances((cfg.img_h, cfg.img_w))
+        p.proposal_boxes = Boxes(synth.make_boxes(2000, cfg.img_h, cfg.img_w, gg, degenerate_frac=0.0).to(dev))
+        p.objectness_logits = torch.randn(2000, generator=gg).to(dev)
+        props.append(p)
+        tgts.append(t)
+    heads = rh.ROIHeads(num_classes=cfg.num_classes)
+
+    def lsp(batched):
+        rh.BATCHED_IMAGES = batched
+        try:
+            return heads.label_and_sample_proposals(props, tgts)
+        finally:
+            rh.BATCHED_IMAGES = True
+
+    res["label_and_sample_proposals"] = {"images": cfg.n_images, "proposals_per_image": 2000, "gt_per_image": 8,
+                                         "ours_batched_ms": timeit(lambda: lsp(True), 10),
+                                         "reference_shaped_loop_eager_ms": timeit(lambda: lsp(False), 5)}
     txt = json.dumps(res, indent=1)
     print(txt)
     if args.out:
