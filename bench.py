@@ -43,6 +43,10 @@ def parse():
     p.add_argument("--workload", default="voc", choices=["voc", "city", "tiny"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--e2e-d2h", choices=["losses", "grads"], default="losses",
+                   help="what the e2e arm reads back every step: the step's result (the three losses, 16 bytes -- in "
+                        "training the gradients stay on the device and feed the backbone's backward), or additionally "
+                        "every gradient the path produces (191 MB at configs[1]; doubles the PCIe traffic)")
     p.add_argument("--tune", action="append", default=[], help="key=value for cddmsl_tune (kernel sweeps)")
     return p.parse_args()
 
@@ -343,7 +347,8 @@ def run_ours(args):
         o_ga = [torch.empty_like(t).pin_memory() for t in h_align]
         o_sc = torch.empty(4).pin_memory()
         h2d = sum(t.numel() * t.element_size() for t in [h_feat, h_rois, hx, hgt] + h_align)
-        d2h = sum(t.numel() * t.element_size() for t in [o_gin, o_dx, o_sc] + o_ga)
+        outs_host = [o_gin, o_dx, o_sc] + o_ga if args.e2e_d2h == "grads" else [o_sc]
+        d2h = sum(t.numel() * t.element_size() for t in outs_host)
 
         # Three streams, double-buffered device inputs: H2D of step i+1 and D2H of step i-1 overlap the compute of
         # step i (what a real input pipeline does).  Every byte still crosses PCIe inside the timed region.
@@ -389,10 +394,10 @@ def run_ours(args):
             torch.autograd.backward([out, lc, li, lr], [out.detach(), one[0], one[0], one[0]])
             sc = torch.stack([lc.detach(), li.detach(), lr.detach(), lc.detach() * 0])
             ev_cmp[b].record(s_cmp)
-            grads = [f.grad, xx.grad, sc] + [t.grad for t in al]
+            grads = [f.grad, xx.grad, sc] + [t.grad for t in al] if args.e2e_d2h == "grads" else [sc]
             with torch.cuda.stream(s_d2h):
                 s_d2h.wait_event(ev_cmp[b])
-                for o, gsrc in zip([o_gin, o_dx, o_sc] + o_ga, grads):
+                for o, gsrc in zip(outs_host, grads):
                     o.copy_(gsrc, non_blocking=True)
                 ev_out[b].record(s_d2h)
             ring[b] = grads
@@ -434,6 +439,8 @@ def run_ours(args):
         e2e = {"value": world * R * k2 / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms2 / k2, "steps": k2,
                "api": "ROIAlign.forward + FastRCNNOutputLayers.forward/losses + caption_consistency_loss + autograd",
+               "d2h": "the three losses (gradients stay in HBM, as in training)" if args.e2e_d2h == "losses"
+                      else "losses + every gradient of the path",
                "pipelining": "H2D(i+1) and D2H(i-1) on side streams overlap compute(i); all copies inside the timed region",
                "numa_bound_cpus": numa_cpus}
     clocks = sampler.stop() if rank == 0 else None
