@@ -21,6 +21,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include <cuda_runtime.h>
+#include <math.h>
 
 #include "common.cuh"
 
@@ -106,13 +107,15 @@ __global__ void nms_gather_kernel(const float4* __restrict__ boxes_all, const in
   scls[i] = cls;
 }
 
-__device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float area_a, float area_b, double thr) {
+__device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float area_a, float area_b, float thr_dn) {
   const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
   const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-  return (double)ovr > thr;  // NaN (0/0) compares false: never suppresses
+  // (double)ovr > thr  <=>  ovr > thr_dn with thr_dn = the largest float <= thr (round_down_threshold): exact, and
+  // keeps the comparison off the FP64 pipe.  NaN (0/0) compares false: never suppresses.
+  return ovr > thr_dn;
 }
 
 // grid (col_blocks, row_blocks), 64 threads; only tiles with col_block >= row_block are computed.
@@ -121,7 +124,7 @@ __device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float a
 // tile) suppresses j — what the scan kernel's ballot fix-point needs.
 __global__ void __launch_bounds__(kTile)
 nms_mask_kernel(const float4* __restrict__ sboxes_all, const int* __restrict__ scls_all,
-                const int32_t* __restrict__ counts, int m_fixed, int m_max, double thr, int col_blocks,
+                const int32_t* __restrict__ counts, int m_fixed, int m_max, float thr, int col_blocks,
                 unsigned long long* __restrict__ mask_all, unsigned long long* __restrict__ coldiag_all) {
   // col_blocks = ceil(m_max / 64): row stride of the mask for every image
   const int img = blockIdx.z;
@@ -328,6 +331,15 @@ static NmsWs carve(void* base, int64_t B, int64_t M) {
   return w;
 }
 
+// The reference compares the fp32 IoU with the threshold in DOUBLE.  For a float v and a double t:
+// (double)v > t  <=>  v > f, where f is the largest float <= t (if t is a float, f == t; otherwise f < t < next(f) and a
+// float exceeds t exactly when it is >= next(f), i.e. > f).  NaN / +-inf thresholds keep their meaning.
+static float round_down_threshold(double t) {
+  float f = (float)t;  // round to nearest
+  if ((double)f > t) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
 // B images, padded to m_max boxes each; counts == nullptr: every image holds exactly m_max boxes (the B = 1 call)
 static int nms_run(const float* boxes, const float* scores, const int64_t* idxs, const int32_t* counts, int B,
                    int m_max, double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep, const NmsWs& w,
@@ -357,7 +369,7 @@ static int nms_run(const float* boxes, const float* scores, const int64_t* idxs,
       m_max, m_max);
   count_launch();
   nms_mask_kernel<<<dim3(col_blocks, col_blocks, B), kTile, 0, stream>>>(w.sboxes, w.scls, counts, m_max, m_max,
-                                                                         iou_threshold, col_blocks, w.mask,
+                                                                         round_down_threshold(iou_threshold), col_blocks, w.mask,
                                                                          w.coldiag);
   count_launch();
   const int smem = col_blocks * 8;
