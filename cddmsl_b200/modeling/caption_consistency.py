@@ -36,16 +36,21 @@ class _CaptionConsistency(torch.autograd.Function):
             dist.all_gather_into_tensor(packed_all, packed, group=group)
         else:
             packed_all = packed.unsqueeze(0)
-        loss, _, _ = ops.align_loss(packed_all, norms, rank, None, False)
-        ctx.save_for_backward(packed_all, norms)
-        ctx.rank = rank
+        # The gradient of the local rows shares the logits / log-sum-exps with the loss: when a gradient will be
+        # asked for it is produced in the same pass (unit upstream scale) instead of re-evaluating S in backward.
+        want = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        loss, da, db = ops.align_loss(packed_all, norms, rank, None, want)
+        if want:
+            ctx.save_for_backward(da, db)
+        ctx.have = want
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
-        packed_all, norms = ctx.saved_tensors
-        _, da, db = ops.align_loss(packed_all, norms, ctx.rank, gloss.reshape(1), True)
-        return da, db, None
+        if not ctx.have:  # forward ran under no_grad-like conditions; nothing was kept
+            raise RuntimeError("caption_consistency_loss: backward without a recorded forward")
+        da, db = ctx.saved_tensors
+        return da * gloss, db * gloss, None
 
 
 def caption_consistency_loss(src: torch.Tensor, tgt: torch.Tensor,

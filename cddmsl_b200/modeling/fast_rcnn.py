@@ -294,9 +294,11 @@ class FastRCNNOutputLayers(nn.Module):
         if fused:
             _, x, w = self._last
             mode, gamma, bgw = self._loss_mode()
+            # when x will need its gradient it is produced by the same pass (the op keeps it for backward)
             loss_cls, _, _, counters = ops.clip_head_loss(x, w, self.cls_bg_score.weight,
                                                           gt_classes.to(scores.device), float(self.temperature),
-                                                          mode, gamma, bgw, None, self.strict_focal_nan, False, False)
+                                                          mode, gamma, bgw, None, self.strict_focal_nan, False,
+                                                          bool(x.requires_grad and torch.is_grad_enabled()))
             _log_classification_stats(scores, gt_classes, counters=counters)
         else:
             _log_classification_stats(scores, gt_classes)

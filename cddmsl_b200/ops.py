@@ -292,19 +292,27 @@ def _(x, weight, bg_weight, gt, temperature, loss_mode, gamma, bg_cls_weight, gr
 
 
 def _loss_setup(ctx, inputs, output):
-    x, weight, bg_weight, gt, temperature, loss_mode, gamma, bg_cls_weight, _gs, strict_nan, _ws_, _wd = inputs
-    ctx.save_for_backward(x, weight, bg_weight, gt)
-    ctx.meta = (temperature, loss_mode, gamma, bg_cls_weight, strict_nan)
+    x, weight, bg_weight, gt, temperature, loss_mode, gamma, bg_cls_weight, gs, strict_nan, _ws_, want_dx = inputs
+    ctx.have_dx = bool(want_dx) and gs is None
+    if ctx.have_dx:
+        ctx.save_for_backward(output[2])  # d loss / d x for a unit upstream gradient, produced by the forward pass
+    else:
+        ctx.save_for_backward(x, weight, bg_weight, gt)
+        ctx.meta = (temperature, loss_mode, gamma, bg_cls_weight, strict_nan)
 
 
 def _loss_bwd(ctx, gloss, gscores, gdx, gstats):
-    x, weight, bg_weight, gt = ctx.saved_tensors
-    t, mode, gamma, bgw, strict = ctx.meta
     dx = None
     if ctx.needs_input_grad[0]:
-        # recompute from x with the upstream scalar folded in: 1 read of x + 1 write of dx
-        _, _, dx, _ = clip_head_loss(x, weight, bg_weight, gt, t, mode, gamma, bgw, gloss.reshape(1), strict,
-                                     False, True)
+        if ctx.have_dx:
+            (dx1,) = ctx.saved_tensors
+            dx = dx1 * gloss
+        else:
+            x, weight, bg_weight, gt = ctx.saved_tensors
+            t, mode, gamma, bgw, strict = ctx.meta
+            # recompute from x with the upstream scalar folded in: 1 read of x + 1 write of dx
+            _, _, dx, _ = clip_head_loss(x, weight, bg_weight, gt, t, mode, gamma, bgw, gloss.reshape(1), strict,
+                                         False, True)
     return (dx,) + (None,) * 11
 
 
