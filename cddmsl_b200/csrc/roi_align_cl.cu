@@ -539,6 +539,63 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
   }
 }
 
+// ---- monotone fast path ------------------------------------------------------------------------------------
+// With adaptive sampling (sampling_ratio == 0) the x-samples of a row are at most one cell apart, so the low column of
+// consecutive samples advances by 0 or 1: the window never restarts.  When the prologue has verified that on the
+// actual table (and rewritten the invalid samples at both ends as zero-weight copies of their nearest valid
+// neighbour), the per-sample step needs ONE test (did the column change?) instead of four nested ones.
+#define CDDMSL_BWD_SAMPLE_MONO(e, COMP)                                                       \
+  if ((e).lo != cur) {                                                                        \
+    bwd_flush<GH1, CPL>(base, (unsigned)cur * Cb, s1, slots, gh, ta0, tb0, nch);              \
+    ta0 = ta1;                                                                                \
+    tb0 = tb1;                                                                                \
+    ta1 = vzero<CPL>();                                                                       \
+    tb1 = vzero<CPL>();                                                                       \
+    cur = (e).lo;                                                                             \
+    curhi = (e).hi;                                                                           \
+  }                                                                                           \
+  _Pragma("unroll") for (int q = 0; q < CPL; ++q) {                                           \
+    ta0.v[q] = fmaf((e).wl, ga[q].COMP, ta0.v[q]);                                            \
+    ta1.v[q] = fmaf((e).wh, ga[q].COMP, ta1.v[q]);                                            \
+    tb0.v[q] = fmaf((e).wl, gb[q].COMP, tb0.v[q]);                                            \
+    tb1.v[q] = fmaf((e).wh, gb[q].COMP, tb1.v[q]);                                            \
+  }
+
+template <int P, bool GH1, int CPL>
+__device__ __forceinline__ void bwd_rows_mono(float* __restrict__ base, const TapE* __restrict__ xtab,
+                                              const YSlots* __restrict__ slots, int gw, int gh, int W, int C,
+                                              const float* __restrict__ grow, int nch) {
+  static_assert(P % 2 == 0, "monotone path: even pooled sizes only");
+  YSlots s1;
+  if (GH1) s1 = slots[0];
+  const unsigned Cb = (unsigned)C * 4u;
+  int cur = xtab[0].lo, curhi = xtab[0].hi;  // entry 0 is valid or a copy of the first valid sample
+  Vec<CPL> ta0 = vzero<CPL>(), ta1 = vzero<CPL>(), tb0 = vzero<CPL>(), tb1 = vzero<CPL>();
+  const TapE* xt = xtab;
+#pragma unroll 1
+  for (int pw = 0; pw < P; pw += 2) {
+    float2 ga[CPL], gb[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const float* gq = grow + (q < nch ? q : 0) * 32 * P * P;
+      ga[q] = *reinterpret_cast<const float2*>(gq + pw);
+      gb[q] = *reinterpret_cast<const float2*>(gq + P + pw);
+    }
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      CDDMSL_BWD_SAMPLE_MONO(e, x)
+    }
+    xt += gw;
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      CDDMSL_BWD_SAMPLE_MONO(e, y)
+    }
+    xt += gw;
+  }
+  bwd_flush<GH1, CPL>(base, (unsigned)cur * Cb, s1, slots, gh, ta0, tb0, nch);
+  if (curhi != cur) bwd_flush<GH1, CPL>(base, (unsigned)curhi * Cb, s1, slots, gh, ta1, tb1, nch);
+}
+
 template <int P, int CPL>
 __global__ void __launch_bounds__(((P + 1) / 2) * 32, 4)
 roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict__ rois, float* __restrict__ gt, int N,
@@ -598,6 +655,42 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
         make_slots(make_tap_entry(g.sh, g.bh, 2 * j, i, g.gh, H, 1.f),
                    2 * j + 1 < P ? make_tap_entry(g.sh, g.bh, 2 * j + 1, i, g.gh, H, 1.f) : null_tap(), W * C);
   }
+  // Monotone check + rewrite of the invalid x-samples (see CDDMSL_BWD_SAMPLE_MONO).  The extra barriers cost nothing
+  // here: the grad tile is still in flight.
+  __shared__ int mono_s[3];  // first valid sample, last valid sample, monotone flag
+  bool mono = false;
+  if (P % 2 == 0 && sampling_ratio <= 0) {
+    const int ns = PE * g.gw;
+    if (threadIdx.x == 0) {
+      mono_s[0] = 0x7fffffff;
+      mono_s[1] = -1;
+      mono_s[2] = 1;
+    }
+    __syncthreads();  // tables written, mono_s initialised
+    for (int t = threadIdx.x; t < ns; t += NT)
+      if (xtab[t].lo >= 0) {
+        atomicMin(&mono_s[0], t);
+        atomicMax(&mono_s[1], t);
+      }
+    __syncthreads();
+    const int sf = mono_s[0], sl = mono_s[1];
+    for (int t = threadIdx.x; t < ns; t += NT) {
+      if (t >= sf && t < sl) {
+        const int a = xtab[t].lo, b = xtab[t + 1].lo;  // valid samples are contiguous: both are valid here
+        if (a < 0 || b < 0 || (b != a && b != xtab[t].hi) || b < a) atomicAnd(&mono_s[2], 0);
+      }
+    }
+    __syncthreads();
+    mono = sl >= 0 && mono_s[2] != 0;
+    if (mono) {
+      for (int t = threadIdx.x; t < ns; t += NT)
+        if (t < sf || t > sl) {
+          TapE e = xtab[t < sf ? sf : sl];
+          e.wl = e.wh = 0.f;
+          xtab[t] = e;
+        }
+    }
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool row_b_exists = 2 * warp + 1 < P;
   for (int c0 = cbeg; c0 < cend; c0 += GC) {
@@ -615,10 +708,20 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
     if (nch > 0) {
       float* base = img + lane;
       const float* grow = G_s + lane * PER + (2 * warp) * P;
-      if (g.gh == 1)
-        bwd_rows<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
-      else
-        bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
+      bool took_mono_path = false;
+      if constexpr (P % 2 == 0) {
+        if (mono) {
+          if (g.gh == 1) bwd_rows_mono<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
+          else bwd_rows_mono<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
+          took_mono_path = true;
+        }
+      }
+      if (!took_mono_path) {
+        if (g.gh == 1)
+          bwd_rows<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
+        else
+          bwd_rows<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch, row_b_exists);
+      }
     }
     if (c0 + GC < cend) {
       __syncthreads();  // every warp is done reading the tile: the next group's copy may overwrite it
