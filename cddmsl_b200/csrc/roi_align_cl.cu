@@ -100,6 +100,45 @@ __device__ __forceinline__ void build_tables(TapE* xtab, TapE* ytab, const RoiGe
   }
 }
 
+// Monotone check of the x-table + rewrite of its invalid samples, used by the fast sample loops.
+// With adaptive sampling (sampling_ratio == 0) the x-samples of a row are at most one cell apart, so the low column of
+// consecutive samples advances by 0 or 1 and the sliding window never restarts.  This verifies that on the ACTUAL
+// table (rounding could break it) and, if it holds, rewrites the invalid samples at both ends (including the padded
+// bins) as zero-weight copies of their nearest valid neighbour, so a sample step needs ONE test (did the column
+// change?) instead of nested validity / slide / restart tests.  Call with the table written but not yet synchronised;
+// on return the (possibly rewritten) table still needs a barrier before it is read.  scratch: 3 ints of shared memory.
+template <int NT>
+__device__ __forceinline__ bool monotone_x_table(TapE* xtab, int ns, int* scratch) {
+  if (threadIdx.x == 0) {
+    scratch[0] = 0x7fffffff;  // first valid sample
+    scratch[1] = -1;          // last valid sample
+    scratch[2] = 1;           // monotone so far
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ns; t += NT)
+    if (xtab[t].lo >= 0) {
+      atomicMin(&scratch[0], t);
+      atomicMax(&scratch[1], t);
+    }
+  __syncthreads();
+  const int sf = scratch[0], sl = scratch[1];
+  for (int t = threadIdx.x; t < ns; t += NT)
+    if (t >= sf && t < sl) {  // valid samples are contiguous in x; anything else clears the flag
+      const int a = xtab[t].lo, b = xtab[t + 1].lo;
+      if (a < 0 || b < a || (b != a && b != xtab[t].hi)) atomicAnd(&scratch[2], 0);
+    }
+  __syncthreads();
+  const bool mono = sl >= 0 && scratch[2] != 0;
+  if (mono)
+    for (int t = threadIdx.x; t < ns; t += NT)
+      if (t < sf || t > sl) {
+        TapE e = xtab[t < sf ? sf : sl];
+        e.wl = e.wh = 0.f;
+        xtab[t] = e;
+      }
+  return mono;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -274,6 +313,60 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
           }
         }
       }
+    }
+  }
+}
+
+// Monotone variant of the sample step (table prepared by monotone_x_table): the window only ever slides.
+#define CDDMSL_FWD_SAMPLE_MONO(e, SA, SB)                                                     \
+  if ((e).lo != cur) {                                                                        \
+    va0 = va1;                                                                                \
+    vb0 = vb1;                                                                                \
+    cur = (e).lo;                                                                             \
+    fwd_column<GH, CPL>(base, (unsigned)(e).hi * Cb, ra, rb, ya, yb, gh, WC, va1, vb1);       \
+  }                                                                                           \
+  vfma<CPL>(SA, (e).wl, va0);                                                                 \
+  vfma<CPL>(SA, (e).wh, va1);                                                                 \
+  vfma<CPL>(SB, (e).wl, vb0);                                                                 \
+  vfma<CPL>(SB, (e).wh, vb1);
+
+template <int P, int GH, int CPL>
+__device__ __forceinline__ void fwd_rows_mono(const float* __restrict__ base, const TapE* __restrict__ xtab,
+                                              const TapE* __restrict__ ytab, int gw, int gh, int W, int C, int row_a,
+                                              float* __restrict__ orow, int kstride) {
+  static_assert(P % 2 == 0, "monotone path: even pooled sizes only");
+  const int WC = W * C;
+  const unsigned Cb = (unsigned)C * 4u;
+  RowTaps<GH> ra, rb;
+  const TapE* ya = ytab + row_a * gh;
+  const TapE* yb = ya + gh;
+  load_row_taps<GH>(ra, base, ya, WC);
+  load_row_taps<GH>(rb, base, yb, WC);
+  // the window starts one column to the left of the first sample with that sample's low column already in slot 1:
+  // the first step slides it into slot 0 and fetches the high column
+  const int first = xtab[0].lo;
+  int cur = first - 1;
+  Vec<CPL> va0 = vzero<CPL>(), vb0 = vzero<CPL>(), va1, vb1;
+  fwd_column<GH, CPL>(base, (unsigned)first * Cb, ra, rb, ya, yb, gh, WC, va1, vb1);
+  const TapE* xt = xtab;
+#pragma unroll 1
+  for (int pw = 0; pw < P; pw += 2) {
+    Vec<CPL> sa0 = vzero<CPL>(), sb0 = vzero<CPL>(), sa1 = vzero<CPL>(), sb1 = vzero<CPL>();
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      CDDMSL_FWD_SAMPLE_MONO(e, sa0, sb0)
+    }
+    xt += gw;
+    for (int ix = 0; ix < gw; ++ix) {
+      const TapE e = xt[ix];
+      CDDMSL_FWD_SAMPLE_MONO(e, sa1, sb1)
+    }
+    xt += gw;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      float* o = orow + k * kstride;
+      *reinterpret_cast<float2*>(o + pw) = make_float2(sa0.v[k], sa1.v[k]);
+      *reinterpret_cast<float2*>(o + P + pw) = make_float2(sb0.v[k], sb1.v[k]);
     }
   }
 }
@@ -655,42 +748,10 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
         make_slots(make_tap_entry(g.sh, g.bh, 2 * j, i, g.gh, H, 1.f),
                    2 * j + 1 < P ? make_tap_entry(g.sh, g.bh, 2 * j + 1, i, g.gh, H, 1.f) : null_tap(), W * C);
   }
-  // Monotone check + rewrite of the invalid x-samples (see CDDMSL_BWD_SAMPLE_MONO).  The extra barriers cost nothing
-  // here: the grad tile is still in flight.
-  __shared__ int mono_s[3];  // first valid sample, last valid sample, monotone flag
+  // Monotone fast path (see monotone_x_table).  Its barriers cost nothing here: the grad tile is still in flight.
+  __shared__ int mono_s[3];
   bool mono = false;
-  if (P % 2 == 0 && sampling_ratio <= 0) {
-    const int ns = PE * g.gw;
-    if (threadIdx.x == 0) {
-      mono_s[0] = 0x7fffffff;
-      mono_s[1] = -1;
-      mono_s[2] = 1;
-    }
-    __syncthreads();  // tables written, mono_s initialised
-    for (int t = threadIdx.x; t < ns; t += NT)
-      if (xtab[t].lo >= 0) {
-        atomicMin(&mono_s[0], t);
-        atomicMax(&mono_s[1], t);
-      }
-    __syncthreads();
-    const int sf = mono_s[0], sl = mono_s[1];
-    for (int t = threadIdx.x; t < ns; t += NT) {
-      if (t >= sf && t < sl) {
-        const int a = xtab[t].lo, b = xtab[t + 1].lo;  // valid samples are contiguous: both are valid here
-        if (a < 0 || b < 0 || (b != a && b != xtab[t].hi) || b < a) atomicAnd(&mono_s[2], 0);
-      }
-    }
-    __syncthreads();
-    mono = sl >= 0 && mono_s[2] != 0;
-    if (mono) {
-      for (int t = threadIdx.x; t < ns; t += NT)
-        if (t < sf || t > sl) {
-          TapE e = xtab[t < sf ? sf : sl];
-          e.wl = e.wh = 0.f;
-          xtab[t] = e;
-        }
-    }
-  }
+  if (P % 2 == 0 && sampling_ratio <= 0) mono = monotone_x_table<NT>(xtab, PE * g.gw, mono_s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool row_b_exists = 2 * warp + 1 < P;
   for (int c0 = cbeg; c0 < cend; c0 += GC) {
@@ -782,6 +843,8 @@ roi_align_fwd_cl_tma_kernel(const float* __restrict__ ft, const float* __restric
     return;
   }
   build_tables<P, NT>(xtab, ytab, g, H, W);
+  __shared__ int mono_s[3];
+  const bool mono = sampling_ratio <= 0 && monotone_x_table<NT>(xtab, PE * g.gw, mono_s);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* wst = stage + warp * (GC * WROW);
@@ -794,7 +857,9 @@ roi_align_fwd_cl_tma_kernel(const float* __restrict__ ft, const float* __restric
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
     }
-    if (g.gh == 1) fwd_rows<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
+    if (mono && g.gh == 1) fwd_rows_mono<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 32 * WROW);
+    else if (mono && g.gh == 2) fwd_rows_mono<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 32 * WROW);
+    else if (g.gh == 1) fwd_rows<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
     else if (g.gh == 2) fwd_rows<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
     else fwd_rows<P, 0, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
