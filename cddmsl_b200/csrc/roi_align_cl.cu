@@ -330,11 +330,12 @@ __device__ __forceinline__ void fwd_rows(const float* __restrict__ base /* image
   vfma<CPL>(SB, (e).wl, vb0);                                                                 \
   vfma<CPL>(SB, (e).wh, vb1);
 
-template <int P, int GH, int CPL>
+template <int P, int GH, int CPL, int GW>
 __device__ __forceinline__ void fwd_rows_mono(const float* __restrict__ base, const TapE* __restrict__ xtab,
-                                              const TapE* __restrict__ ytab, int gw, int gh, int W, int C, int row_a,
+                                              const TapE* __restrict__ ytab, int gw_, int gh, int W, int C, int row_a,
                                               float* __restrict__ orow, int kstride) {
   static_assert(P % 2 == 0, "monotone path: even pooled sizes only");
+  const int gw = GW > 0 ? GW : gw_;  // 1 or 2 samples per bin known at compile time: the sample loops unroll away
   const int WC = W * C;
   const unsigned Cb = (unsigned)C * 4u;
   RowTaps<GH> ra, rb;
@@ -654,11 +655,12 @@ __device__ __forceinline__ void bwd_rows(float* __restrict__ base, const TapE* _
     tb1.v[q] = fmaf((e).wh, gb[q].COMP, tb1.v[q]);                                            \
   }
 
-template <int P, bool GH1, int CPL>
+template <int P, bool GH1, int CPL, int GW>
 __device__ __forceinline__ void bwd_rows_mono(float* __restrict__ base, const TapE* __restrict__ xtab,
-                                              const YSlots* __restrict__ slots, int gw, int gh, int W, int C,
+                                              const YSlots* __restrict__ slots, int gw_, int gh, int W, int C,
                                               const float* __restrict__ grow, int nch) {
   static_assert(P % 2 == 0, "monotone path: even pooled sizes only");
+  const int gw = GW > 0 ? GW : gw_;
   YSlots s1;
   if (GH1) s1 = slots[0];
   const unsigned Cb = (unsigned)C * 4u;
@@ -772,8 +774,14 @@ roi_align_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict_
       bool took_mono_path = false;
       if constexpr (P % 2 == 0) {
         if (mono) {
-          if (g.gh == 1) bwd_rows_mono<P, true, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
-          else bwd_rows_mono<P, false, CPL>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch);
+#define CDDMSL_BWD_MONO(GH1V, GWV) \
+  bwd_rows_mono<P, GH1V, CPL, GWV>(base, xtab, yslots + warp * kMaxG, g.gw, g.gh, W, C, grow, nch)
+          // (more compile-time sample counts were measured on the backward: slower -- the kernel is issue-bound and
+          //  the extra variants cost more instruction-cache misses than their unrolled loops save)
+          if (g.gh == 1 && g.gw == 1) CDDMSL_BWD_MONO(true, 1);
+          else if (g.gh == 1) CDDMSL_BWD_MONO(true, 0);
+          else CDDMSL_BWD_MONO(false, 0);
+#undef CDDMSL_BWD_MONO
           took_mono_path = true;
         }
       }
@@ -857,8 +865,18 @@ roi_align_fwd_cl_tma_kernel(const float* __restrict__ ft, const float* __restric
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
     }
-    if (mono && g.gh == 1) fwd_rows_mono<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 32 * WROW);
-    else if (mono && g.gh == 2) fwd_rows_mono<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 32 * WROW);
+#define CDDMSL_FWD_MONO(GHV, GWV) \
+  fwd_rows_mono<P, GHV, CPL, GWV>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 32 * WROW)
+    if (mono && g.gh == 1) {
+      if (g.gw == 1) CDDMSL_FWD_MONO(1, 1);
+      else if (g.gw == 2) CDDMSL_FWD_MONO(1, 2);
+      else CDDMSL_FWD_MONO(1, 0);
+    } else if (mono && g.gh == 2) {
+      if (g.gw == 1) CDDMSL_FWD_MONO(2, 1);
+      else if (g.gw == 2) CDDMSL_FWD_MONO(2, 2);
+      else CDDMSL_FWD_MONO(2, 0);
+    }
+#undef CDDMSL_FWD_MONO
     else if (g.gh == 1) fwd_rows<P, 1, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
     else if (g.gh == 2) fwd_rows<P, 2, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
     else fwd_rows<P, 0, CPL>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, CPL, 32 * WROW);
