@@ -372,6 +372,77 @@ __device__ __forceinline__ void fwd_rows_mono(const float* __restrict__ base, co
   }
 }
 
+// gh == 1 monotone path with the NEXT footprint column's raw loads kept in flight: the kernel is bound by the latency
+// of first-touch lines (long-scoreboard 6.5 cycles per issued instruction), and with one row sample per bin a column is
+// only four loads per channel -- room for eight more registers.
+template <int P, int CPL, int GW>
+__device__ __forceinline__ void fwd_rows_mono_pf(const float* __restrict__ base, const TapE* __restrict__ xtab,
+                                                 const TapE* __restrict__ ytab, int gw_, int W, int C, int row_a,
+                                                 float* __restrict__ orow, int kstride) {
+  static_assert(P % 2 == 0, "monotone path: even pooled sizes only");
+  const int gw = GW > 0 ? GW : gw_;
+  const int WC = W * C;
+  const unsigned Cb = (unsigned)C * 4u;
+  RowTaps<1> ra, rb;
+  load_row_taps<1>(ra, base, ytab + row_a, WC);
+  load_row_taps<1>(rb, base, ytab + row_a + 1, WC);
+  Vec<CPL> p0, p1, p2, p3;  // raw rows (a.lo, a.hi, b.lo, b.hi) of the prefetched column
+#define CDDMSL_PF_ISSUE(col)                      \
+  {                                               \
+    const unsigned xo_ = (unsigned)(col) * Cb;    \
+    p0 = vload_off<CPL>(ra.plo[0], xo_);          \
+    p1 = vload_off<CPL>(ra.phi[0], xo_);          \
+    p2 = vload_off<CPL>(rb.plo[0], xo_);          \
+    p3 = vload_off<CPL>(rb.phi[0], xo_);          \
+  }
+#define CDDMSL_PF_BLEND(va, vb)       \
+  {                                   \
+    va = vzero<CPL>();                \
+    vb = vzero<CPL>();                \
+    vfma<CPL>(va, ra.wl[0], p0);      \
+    vfma<CPL>(va, ra.wh[0], p1);      \
+    vfma<CPL>(vb, rb.wl[0], p2);      \
+    vfma<CPL>(vb, rb.wh[0], p3);      \
+  }
+  const int first = xtab[0].lo;
+  int cur = first - 1;
+  Vec<CPL> va0 = vzero<CPL>(), vb0 = vzero<CPL>(), va1, vb1;
+  CDDMSL_PF_ISSUE(first)
+  CDDMSL_PF_BLEND(va1, vb1)
+  CDDMSL_PF_ISSUE(min(first + 1, W - 1))
+  const TapE* xt = xtab;
+#pragma unroll 1
+  for (int pw = 0; pw < P; pw += 2) {
+    Vec<CPL> s[2][2] = {{vzero<CPL>(), vzero<CPL>()}, {vzero<CPL>(), vzero<CPL>()}};  // [bin][row]
+#pragma unroll
+    for (int bin = 0; bin < 2; ++bin) {
+      for (int ix = 0; ix < gw; ++ix) {
+        const TapE e = xt[ix];
+        if (e.lo != cur) {  // slide: the prefetched column is exactly e.hi
+          va0 = va1;
+          vb0 = vb1;
+          cur = e.lo;
+          CDDMSL_PF_BLEND(va1, vb1)
+          CDDMSL_PF_ISSUE(min(e.hi + 1, W - 1))
+        }
+        vfma<CPL>(s[bin][0], e.wl, va0);
+        vfma<CPL>(s[bin][0], e.wh, va1);
+        vfma<CPL>(s[bin][1], e.wl, vb0);
+        vfma<CPL>(s[bin][1], e.wh, vb1);
+      }
+      xt += gw;
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      float* o = orow + k * kstride;
+      *reinterpret_cast<float2*>(o + pw) = make_float2(s[0][0].v[k], s[1][0].v[k]);
+      *reinterpret_cast<float2*>(o + P + pw) = make_float2(s[0][1].v[k], s[1][1].v[k]);
+    }
+  }
+#undef CDDMSL_PF_ISSUE
+#undef CDDMSL_PF_BLEND
+}
+
 __device__ void fwd_direct_any(const float* __restrict__ in, float* __restrict__ out_roi, int c0, int nch, int C, int H,
                                int W, int PH, int PW, const RoiGeom& g, int nthreads) {
   const int per = PH * PW;
@@ -868,9 +939,12 @@ roi_align_fwd_cl_tma_kernel(const float* __restrict__ ft, const float* __restric
 #define CDDMSL_FWD_MONO(GHV, GWV) \
   fwd_rows_mono<P, GHV, CPL, GWV>(base, xtab, ytab, g.gw, g.gh, W, C, 2 * warp, orow, 32 * WROW)
     if (mono && g.gh == 1) {
-      if (g.gw == 1) CDDMSL_FWD_MONO(1, 1);
-      else if (g.gw == 2) CDDMSL_FWD_MONO(1, 2);
-      else CDDMSL_FWD_MONO(1, 0);
+#define CDDMSL_FWD_MONO_PF(GWV) \
+  fwd_rows_mono_pf<P, CPL, GWV>(base, xtab, ytab, g.gw, W, C, 2 * warp, orow, 32 * WROW)
+      if (g.gw == 1) CDDMSL_FWD_MONO_PF(1);
+      else if (g.gw == 2) CDDMSL_FWD_MONO_PF(2);
+      else CDDMSL_FWD_MONO_PF(0);
+#undef CDDMSL_FWD_MONO_PF
     } else if (mono && g.gh == 2) {
       if (g.gw == 1) CDDMSL_FWD_MONO(2, 1);
       else if (g.gw == 2) CDDMSL_FWD_MONO(2, 2);
