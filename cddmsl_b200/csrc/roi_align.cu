@@ -417,6 +417,14 @@ bool roi_cl_eligible(int N, int C, int H, int W, int PH, int PW);
 size_t roi_cl_workspace_bytes(int N, int C, int H, int W);
 int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, int P,
                      float scale, int sampling_ratio, int aligned, float* ft, cudaStream_t stream);
+// plane-resident path (roi_align_pr.cu): map slices stay in shared memory, lanes are output columns
+bool roi_pr_eligible(int N, int C, int H, int W, int R, int P, int bit);
+size_t roi_pr_workspace_bytes(int N, int R);
+int roi_align_fwd_pr(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
+int roi_align_bwd_pr(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
+int tune_roi_pr(const char* key, int value);
 int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
                      float scale, int sampling_ratio, int aligned, float* gt, cudaStream_t stream);
 
@@ -430,8 +438,14 @@ int tune_roi(const char* key, int value) {
   else if (!strcmp(key, "roi_bwd_cpl")) g_bwd_cpl = value;
   else if (!strcmp(key, "roi_gpc")) g_roi_gpc = value;
   else if (!strcmp(key, "roi_tma")) g_roi_tma = value;
-  else return 0;
+  else return tune_roi_pr(key, value);
   return 1;
+}
+
+static size_t roi_workspace_bytes(int N, int C, int H, int W, int R) {
+  N = N > 0 ? N : 0, C = C > 0 ? C : 0, H = H > 0 ? H : 0, W = W > 0 ? W : 0, R = R > 0 ? R : 0;
+  const size_t a = roi_cl_workspace_bytes(N, C, H, W), b = roi_pr_workspace_bytes(N, R);
+  return (a > b ? a : b) + 256;
 }
 
 }  // namespace cddmsl
@@ -439,8 +453,7 @@ int tune_roi(const char* key, int value) {
 using namespace cddmsl;
 
 extern "C" size_t cddmsl_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int R) {
-  (void)R;
-  return roi_cl_workspace_bytes(N > 0 ? N : 0, C > 0 ? C : 0, H > 0 ? H : 0, W > 0 ? W : 0) + 256;
+  return roi_workspace_bytes(N, C, H, W, R);
 }
 
 extern "C" int cddmsl_roi_align_fwd(const float* in, const float* rois, float* out, int N, int C, int H, int W,
@@ -456,6 +469,10 @@ extern "C" int cddmsl_roi_align_fwd(const float* in, const float* rois, float* o
   }
   if (!in) return CDDMSL_EINVAL;
   if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return CDDMSL_EALIGN;
+  const bool ws_ok = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0;
+  if (PH == PW && ws_ok && workspace_bytes >= roi_pr_workspace_bytes(N, R) && roi_pr_eligible(N, C, H, W, R, PH, 1))
+    return roi_align_fwd_pr(in, rois, out, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned, workspace,
+                            stream);
   if (g_use_cl && roi_cl_eligible(N, C, H, W, PH, PW) && workspace &&
       workspace_bytes >= roi_cl_workspace_bytes(N, C, H, W) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
     return roi_align_fwd_cl(in, rois, out, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned,
@@ -483,11 +500,7 @@ extern "C" int cddmsl_roi_align_fwd(const float* in, const float* rois, float* o
 }
 
 extern "C" size_t cddmsl_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R) {
-  (void)C;
-  (void)H;
-  (void)W;
-  (void)R;
-  return roi_cl_workspace_bytes(N > 0 ? N : 0, C > 0 ? C : 0, H > 0 ? H : 0, W > 0 ? W : 0) + 256;
+  return roi_workspace_bytes(N, C, H, W, R);
 }
 
 extern "C" int cddmsl_roi_align_bwd(const float* gout, const float* rois, float* gin, int N, int C, int H, int W,
