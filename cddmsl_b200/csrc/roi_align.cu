@@ -424,6 +424,7 @@ int roi_align_fwd_pr(const float* in, const float* rois, float* out, int N, int 
                      float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
 int roi_align_bwd_pr(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
                      float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
+bool roi_pr_bwd_eligible(int N, int C, int H, int W, int R, int P);
 int tune_roi_pr(const char* key, int value);
 int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
                      float scale, int sampling_ratio, int aligned, float* gt, cudaStream_t stream);
@@ -517,6 +518,10 @@ extern "C" int cddmsl_roi_align_bwd(const float* gout, const float* rois, float*
   }
   if (!gout || !rois) return CDDMSL_EINVAL;
   if ((reinterpret_cast<uintptr_t>(gout) & 15) != 0) return CDDMSL_EALIGN;
+  if (PH == PW && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+      workspace_bytes >= roi_pr_workspace_bytes(N, R) && roi_pr_bwd_eligible(N, C, H, W, R, PH))
+    return roi_align_bwd_pr(gout, rois, gin, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned, workspace,
+                            stream);
   if (g_use_cl && roi_cl_eligible(N, C, H, W, PH, PW) && workspace &&
       workspace_bytes >= roi_cl_workspace_bytes(N, C, H, W) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
     return roi_align_bwd_cl(gout, rois, gin, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned,

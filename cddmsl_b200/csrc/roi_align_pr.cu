@@ -48,9 +48,11 @@ struct __align__(16) PrRecB {
 static_assert(sizeof(PrRecA) == 32 && sizeof(PrRecB) == 32, "record halves are moved in 16-byte pieces");
 
 enum { PR_ZERO = 0, PR_BAND = 1, PR_DIRECT = 3 };
-struct __align__(16) PrHdr {  // first 16 bytes of a block's slot 0
+struct __align__(16) PrHdr {  // slot 0 of a block
   int cls, nxmax, nymax, roi;
+  int x0, fw, nimax, pad;  // backward: first footprint column, footprint width, most bins sharing one column
 };
+static_assert(sizeof(PrHdr) == 32, "header fills slot 0");
 // One RoI = one block of 29 slots: [header][x bins 0..13][y bins 0..13]; blocks are stored in (image, cost bucket)
 // order, so a chunk of an image's RoIs is a contiguous run of blocks.
 constexpr int kPrBlockSlots = 29;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) pr_plan_fill_kernel(const float* __restri
   PrRecB* blkB = plan.blocksB + (size_t)pos * kPrBlockSlots;
   const int axis = lane >= P ? 1 : 0;  // 0: x bins (lanes 0..P-1), 1: y bins (lanes P..2P-1)
   const int p = lane - axis * P;
-  int n = 0;
+  int n = 0, rstart_l = 0;
   bool overflow = false;
   if (lane < 2 * P) {
     int rstart = 0, rn = 0;
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(256) pr_plan_fill_kernel(const float* __restri
             rw[t.hi - first] += t.wh * sc;
           }
           rstart = first;
+          rstart_l = first;
           rn = n;
         }
       }
@@ -239,12 +242,34 @@ __global__ void __launch_bounds__(256) pr_plan_fill_kernel(const float* __restri
     nx = max(nx, __shfl_xor_sync(0xffffffffu, nx, o));
     ny = max(ny, __shfl_xor_sync(0xffffffffu, ny, o));
   }
+  // backward facts of the x bands: footprint [x0, x0 + fw) and the largest number of bins that touch one column
+  const bool xl = lane < P && n > 0 && !overflow;
+  const int my_s = xl ? rstart_l : 0x7fffffff, my_e = xl ? rstart_l + n : 0;
+  int x0 = my_s, x1 = my_e, ni = 0;
+  for (int j = 0; j < min(nx, kPrNW); ++j) {  // (warp-uniform trip count) how many bins cover column rstart_l + j
+    int c = 0;
+    for (int q = 0; q < P; ++q) {
+      const int s2 = __shfl_sync(0xffffffffu, my_s, q), e2 = __shfl_sync(0xffffffffu, my_e, q);
+      c += (rstart_l + j >= s2 && rstart_l + j < e2) ? 1 : 0;
+    }
+    if (xl && j < n) ni = max(ni, c);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+    x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    ni = max(ni, __shfl_xor_sync(0xffffffffu, ni, o));
+  }
   if (lane == 31) {
     PrHdr h;
     h.roi = r;
     h.nxmax = nx;
     h.nymax = ny;
     h.cls = !valid ? PR_ZERO : (!mergeable || ovf) ? PR_DIRECT : PR_BAND;
+    h.x0 = x1 > 0 ? x0 : 0;
+    h.fw = x1 > 0 ? x1 - x0 : 0;
+    h.nimax = ni;
+    h.pad = 0;
     *reinterpret_cast<PrHdr*>(blkA) = h;
   }
 }
@@ -333,17 +358,17 @@ struct PrTileSink {
     off = dbg & 1;
   }
   __device__ __forceinline__ void start(int roi) {
-    if (pending) {  // the tile is about to be rewritten: the copy engine must have read it
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      pending = false;
-    }
     op = tp;
     gdst = out + ((size_t)roi * C + cbase) * M::PER;
   }
   // one output row: v(k) yields the value of channel pass k
   template <class F>
   __device__ __forceinline__ void row(F&& v) {
+    if (pending) {  // first row of a RoI: the tile is about to be rewritten, the copy engine must have read it
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      pending = false;
+    }
 #pragma unroll
     for (int k = 0; k < CPL; ++k) op[M::koff(k) * M::PER] = v(k);
     op += P;
@@ -404,9 +429,11 @@ __device__ __forceinline__ void pr_fwd_win2(const float* a0, const float (&wx)[N
   for (int k = 0; k < CPL; ++k) hA[k] = hB[k] = 0.f;
   int cy = -0x40000000;
   bool flip = false;  // false: A = row cy, B = row cy + 1
+  int4 yn = *reinterpret_cast<const int4*>(yrec);  // warp-uniform; the next record is fetched a row ahead
 #pragma unroll 1
   for (int ph = 0; ph < P; ++ph) {
-    const int4 yr = *reinterpret_cast<const int4*>(yrec + ph * 8);  // warp-uniform
+    const int4 yr = yn;
+    yn = *reinterpret_cast<const int4*>(yrec + min(ph + 1, P - 1) * 8);
     const int ys = yr.x;
     if (yr.y > 0 && ys != cy) {
       const float* ra = a0 + (ys + 1) * RS;
@@ -446,10 +473,14 @@ __device__ __forceinline__ void pr_fwd_win(const float* a0, const float (&wx)[NX
 #pragma unroll
     for (int k = 0; k < CPL; ++k) hw[r][k] = 0.f;
   int cy = -0x40000000;
+  int4 na = *reinterpret_cast<const int4*>(yrec);
+  float4 nb = *reinterpret_cast<const float4*>(yrec + 4);
 #pragma unroll 1
   for (int ph = 0; ph < P; ++ph) {
-    const int4 ca = *reinterpret_cast<const int4*>(yrec + ph * 8);
-    const float4 cb = *reinterpret_cast<const float4*>(yrec + ph * 8 + 4);
+    const int4 ca = na;
+    const float4 cb = nb;
+    na = *reinterpret_cast<const int4*>(yrec + min(ph + 1, P - 1) * 8);
+    nb = *reinterpret_cast<const float4*>(yrec + min(ph + 1, P - 1) * 8 + 4);
     const int ys = ca.x;
     if (ca.y > 0 && ys != cy) {
       int d = ys - cy;
@@ -631,9 +662,363 @@ roi_align_fwd_pr_kernel(const float* __restrict__ in, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// Transpose of the forward.  Global traffic: the compulsory stream of the pooled gradient (one 1-D bulk load of the
+// RoI's contiguous [CH][196] tile per visit, mbarrier completion) and ONE coalesced red.global.add per (footprint
+// row, channel) into the zeroed NCHW gradient map -- fh*fw reductions per RoI and channel, all of them 64-byte
+// runs on an L2-resident image (the round-1 kernel issued ~(fh+14)*fw and moved 12 GB through the L2 atomic units).
+// Per RoI a warp
+//   1. accumulates U = Ay^T G in registers with the lanes on the BINS (the y bands are warp-uniform): a window of WIN
+//      footprint rows per channel pass; a row leaves the window complete;
+//   2. transposes the completed row so that the lanes are on the footprint COLUMNS: the 4 channel passes of a bin go
+//      to a scratch line as one float4, and lane (column x) sums w * u4 over the bins whose band covers x -- the
+//      inverse of the x bands, built once per visit into a small per-warp table.  Narrow footprints (most RoIs are
+//      only a few cells wide, so a column is shared by up to 14 bins) split a column's bins over 2-8 lanes and finish
+//      with a shuffle reduction; wide footprints take several 16-column passes.
+constexpr int kPrBwdWarps = 16;
+constexpr int kPrBwdThreads = kPrBwdWarps * 32;
+constexpr int kPrTblV = 144;                      // virtual columns (lane slots) the inverse table holds
+constexpr int kPrTblFloats = 576;                 // weights: nv * nps <= 576 (16 x 14 narrow, 129 x 4 wide)
+constexpr int kPrScratch = 2 * 16 * 4;            // [SLOTS][16 bins][4 passes]
+
+__device__ __forceinline__ void pr_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pr_smem_u32(bar)));
+}
+__device__ __forceinline__ void pr_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pr_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   pr_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(pr_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void pr_mbar_wait(uint64_t* bar, uint32_t parity) {  // bounded: a protocol bug must trap
+  const uint32_t a = pr_smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void pr_red_global(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// Per-warp state of the horizontal (transposed) pass.
+template <int CPL>
+struct PrBwdCtx {
+  float* gimg;      // gin + (img * C + cbase + D * slot) * H * W: this slot's first channel plane
+  float* scratch;   // [SLOTS][16][4]
+  const float* tbl; // inverse x table: [virtual column][nps] weights
+  const int* tpa;   // [virtual column] first bin of the lane's (shifted) window of bins
+  int HW, W, H, x0, fw, nps, nv, logl, slot, xi, p;
+  bool act[CPL];    // channel pass exists (ragged last group)
+};
+
+// gin[y][x0 + col] += sum_i tbl[v][i] * u[tpa[v] + i] for every footprint column, all CPL channel passes
+template <int CPL>
+__device__ __forceinline__ void pr_bwd_flush(const PrBwdCtx<CPL>& c, int y, const float (&u)[CPL]) {
+  using M = PrMap<14, CPL>;
+  if (y < 0 || y >= c.H) return;  // rows beyond the map only ever collect zero weights
+  float* sline = c.scratch + c.slot * 64;
+  if (CPL == 4) {
+    *reinterpret_cast<float4*>(sline + c.p * 4) = make_float4(u[0], u[1 % CPL], u[2 % CPL], u[3 % CPL]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) sline[c.p * 4 + k] = u[k];
+  }
+  __syncwarp();
+  float* grow = c.gimg + (size_t)y * c.W + c.x0;
+  for (int v = c.xi; v < c.nv; v += 16) {
+    const float* wt = c.tbl + v * c.nps;
+    const float* sc = sline + c.tpa[v] * 4;
+    float t[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) t[k] = 0.f;
+    for (int i = 0; i < c.nps; ++i) {
+      const float w = wt[i];
+      if (CPL == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(sc + 4 * i);
+        t[0] = fmaf(w, q.x, t[0]);
+        t[1 % CPL] = fmaf(w, q.y, t[1 % CPL]);
+        t[2 % CPL] = fmaf(w, q.z, t[2 % CPL]);
+        t[3 % CPL] = fmaf(w, q.w, t[3 % CPL]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) t[k] = fmaf(w, sc[4 * i + k], t[k]);
+      }
+    }
+    for (int s = 1; s < (1 << c.logl); s <<= 1) {  // the lanes that share a column
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], s);
+    }
+    const int col = v >> c.logl;
+    if ((v & ((1 << c.logl) - 1)) == 0 && col < c.fw) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k)
+        if (c.act[k]) pr_red_global(grow + (size_t)M::koff(k) * c.HW + col, t[k]);
+    }
+  }
+  __syncwarp();  // scratch is rewritten by the next flush
+}
+
+// Vertical pass: window of WIN footprint rows (rows cy .. cy+WIN-1) of U per channel pass; WIN >= the tallest band.
+template <int CPL, int WIN>
+__device__ __forceinline__ void pr_bwd_win(const PrBwdCtx<CPL>& c, const float* gp /* tile + slot/bin */,
+                                           const float* yrec) {
+  using M = PrMap<14, CPL>;
+  float acc[WIN][CPL];
+#pragma unroll
+  for (int r = 0; r < WIN; ++r)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[r][k] = 0.f;
+  int cy = 0;
+  bool open = false;
+  auto advance = [&]() {  // row cy is complete
+    pr_bwd_flush<CPL>(c, cy, acc[0]);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+#pragma unroll
+      for (int r = 0; r + 1 < WIN; ++r) acc[r][k] = acc[r + 1][k];
+      acc[WIN - 1][k] = 0.f;
+    }
+    ++cy;
+  };
+#pragma unroll 1
+  for (int ph = 0; ph < 14; ++ph, gp += 14) {
+    const int4 ca = *reinterpret_cast<const int4*>(yrec + ph * 8);
+    const float4 cb = *reinterpret_cast<const float4*>(yrec + ph * 8 + 4);
+    float g[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) g[k] = gp[M::koff(k) * 196];
+    if (ca.y > 0) {
+      if (!open) {
+        cy = ca.x;
+        open = true;
+      }
+      if (ca.x - cy > WIN) {  // (never with adaptive sampling) a gap: drain, restart at the new band
+        for (int r = 0; r < WIN; ++r) advance();
+        cy = ca.x;
+      }
+      while (cy < ca.x) advance();
+      float wy[WIN];
+      wy[0] = __int_as_float(ca.z);
+      wy[1] = __int_as_float(ca.w);
+      if (WIN > 2) wy[2] = cb.x;
+      if (WIN > 3) wy[WIN > 3 ? 3 : 0] = cb.y;
+      if (WIN > 4) wy[WIN > 4 ? 4 : 0] = cb.z;
+      if (WIN > 5) wy[WIN > 5 ? 5 : 0] = cb.w;
+#pragma unroll
+      for (int r = 0; r < WIN; ++r)
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) acc[r][k] = fmaf(wy[r], g[k], acc[r][k]);
+    }
+  }
+  if (open)
+    for (int r = 0; r < WIN; ++r) advance();
+}
+
+// Bands taller than the window templates: every (output row, band row) pair is flushed on its own.
+template <int CPL>
+__device__ __forceinline__ void pr_bwd_gen(const PrBwdCtx<CPL>& c, const float* gp, const float* yrec,
+                                           const PrRecB* yrecB) {
+  using M = PrMap<14, CPL>;
+#pragma unroll 1
+  for (int ph = 0; ph < 14; ++ph, gp += 14) {
+    const float* yr = yrec + ph * 8;
+    const int ys = __float_as_int(yr[0]), ny = __float_as_int(yr[1]);
+    float g[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) g[k] = gp[M::koff(k) * 196];
+    for (int r = 0; r < ny; ++r) {
+      const float wy = r < 6 ? yr[2 + r] : __ldg(&yrecB[ph].w[r - 6]);
+      float u[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) u[k] = wy * g[k];
+      pr_bwd_flush<CPL>(c, ys + r, u);
+    }
+  }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kPrBwdThreads, 1)
+roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict__ rois, float* __restrict__ gin,
+                        PrPlan plan, int N, int C, int H, int W, int ngroups, float scale, int sampling_ratio,
+                        int aligned, int dbg) {
+  constexpr int P = 14;
+  using M = PrMap<P, CPL>;
+  constexpr int CH = M::CH, D = M::D, PER = 196;
+  extern __shared__ __align__(128) float smem[];
+  float* wrec = smem;                                                      // [warps][2][232]: RoI blocks (A halves)
+  float* tiles = wrec + kPrBwdWarps * 2 * kPrBlockFloats;                  // [warps][CH][196]: pooled-gradient tiles
+  float* tbls = tiles + kPrBwdWarps * M::STG;                              // [warps][kPrTblFloats]
+  int* tpas = reinterpret_cast<int*>(tbls + kPrBwdWarps * kPrTblFloats);   // [warps][kPrTblV]
+  float* scr = reinterpret_cast<float*>(tpas + kPrBwdWarps * kPrTblV);     // [warps][kPrScratch]
+  __shared__ int s_unit, s_next;
+  __shared__ __align__(8) uint64_t bars[kPrBwdWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = lane >> 4;
+  const int p = min(lane & 15, P - 1);  // idle lanes mirror the slot's last bin
+  float* wbuf = wrec + warp * (2 * kPrBlockFloats);
+  float* tile = tiles + warp * M::STG;
+  float* mytbl = tbls + warp * kPrTblFloats;
+  int* mytpa = tpas + warp * kPrTblV;
+  uint64_t* bar = &bars[warp];
+  if (lane == 0) pr_mbar_init(bar);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t phase = 0;
+  const int HW = H * W;
+  PrBwdCtx<CPL> ctx;
+  ctx.scratch = scr + warp * kPrScratch;
+  ctx.tbl = mytbl;
+  ctx.tpa = mytpa;
+  ctx.HW = HW;
+  ctx.W = W;
+  ctx.H = H;
+  ctx.slot = slot;
+  ctx.xi = lane & 15;
+  ctx.p = p;
+  const int nunits = plan.counter[1] * ngroups;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_unit = atomicAdd(&plan.counter[2], 1);
+      s_next = 0;
+    }
+    __syncthreads();
+    const int u = s_unit;
+    if (u >= nunits) break;
+    const int j = u / ngroups, cg = u - j * ngroups;
+    const PrChunk ck = plan.chunks[j];
+    const int cbase = cg * CH, nch = min(CH, C - cbase), nroi = ck.end - ck.begin;
+    const uint32_t tile_bytes = (uint32_t)nch * PER * 4u;
+    ctx.gimg = gin + ((size_t)ck.img * C + cbase + D * slot) * HW;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) ctx.act[k] = (M::koff(k) + D * slot) < nch && !(dbg & 1);
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&s_next, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i < nroi) pr_issue_block(wbuf, plan.blocksA + (size_t)(ck.begin + i) * kPrBlockSlots, lane);
+    pr_commit();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (i < nroi && lane == 0) {
+      const int roi = reinterpret_cast<const PrHdr*>(wbuf)->roi;
+      pr_bulk_load(tile, gout + ((size_t)roi * C + cbase) * PER, tile_bytes, bar);
+    }
+    int buf = 0;
+    while (i < nroi) {
+      int inext = 0;
+      if (lane == 0) inext = atomicAdd(&s_next, 1);
+      inext = __shfl_sync(0xffffffffu, inext, 0);
+      if (inext < nroi)
+        pr_issue_block(wbuf + (buf ^ 1) * kPrBlockFloats, plan.blocksA + (size_t)(ck.begin + inext) * kPrBlockSlots,
+                       lane);
+      pr_commit();
+      const float* blk = wbuf + buf * kPrBlockFloats;
+      const PrHdr hd = *reinterpret_cast<const PrHdr*>(blk);
+      const float* yrec = blk + 15 * 8;
+      const PrRecB* blkB = plan.blocksB + (size_t)(ck.begin + i) * kPrBlockSlots;
+      const bool small = hd.nxmax <= 2 && hd.nymax <= 2;
+      // lanes per column (narrow footprints) and the table geometry
+      int logl = 0;
+      if (hd.fw <= 8) logl = hd.fw <= 2 ? 3 : hd.fw <= 4 ? 2 : 1;
+      const int nps = (hd.nimax + (1 << logl) - 1) >> logl;   // bins per lane
+      const int nv = hd.fw <= 16 ? 16 : hd.fw;                 // virtual columns
+      const bool band = hd.cls == PR_BAND && !((dbg & 2) && !small) && !((dbg & 4) && small) && hd.fw > 0 &&
+                        nv <= kPrTblV && nv * nps <= kPrTblFloats && nps <= P;
+      if (band) {
+        // ---- inverse of the x bands: for every (column, lane part) the contiguous bins whose band covers it ------
+        ctx.x0 = hd.x0;
+        ctx.fw = hd.fw;
+        ctx.nps = nps;
+        ctx.nv = nv;
+        ctx.logl = logl;
+        const int shift_max = P - nps;  // windows of nps bins are shifted left to stay inside 0..13
+        for (int v = lane; v < nv; v += 32) {
+          float* wt = mytbl + v * nps;
+          for (int q = 0; q < nps; ++q) wt[q] = 0.f;
+          const int col = v >> logl, part = v & ((1 << logl) - 1);
+          const int x = hd.x0 + col;
+          int pa = -1, seen = 0;
+          if (col < hd.fw)
+            for (int pw = 0; pw < P; ++pw) {
+              const float* xr = blk + (1 + pw) * 8;
+              const int xs = __float_as_int(xr[0]), n = __float_as_int(xr[1]);
+              const int jx = x - xs;
+              if (jx >= 0 && jx < n) {
+                if (seen >= part * nps && seen < (part + 1) * nps) {
+                  if (pa < 0) pa = min(pw, shift_max);
+                  wt[pw - pa] = jx < 6 ? xr[2 + jx] : __ldg(&blkB[1 + pw].w[jx - 6]);
+                }
+                ++seen;
+              }
+            }
+          mytpa[v] = pa < 0 ? 0 : pa;
+        }
+      }
+      pr_mbar_wait(bar, phase);  // this RoI's gradient tile has landed
+      phase ^= 1u;
+      __syncwarp();
+      const float* gp = tile + (D * slot) * PER + p;
+      if (band) {
+        if (hd.nymax <= 2) pr_bwd_win<CPL, 2>(ctx, gp, yrec);
+        else if (hd.nymax <= 4) pr_bwd_win<CPL, 4>(ctx, gp, yrec);
+        else pr_bwd_gen<CPL>(ctx, gp, yrec, blkB + 15);
+      } else if (hd.cls == PR_DIRECT || (hd.cls == PR_BAND && !(dbg & 6))) {
+        // ---- per-sample scatter in the reference's order (sparse / huge sampling grids): rare ------------------
+        const RoiGeom g = roi_geom(rois + (size_t)hd.roi * 5, scale, aligned, P, P, sampling_ratio, H, W);
+        if ((lane & 15) < P) {
+#pragma unroll 1
+          for (int ph = 0; ph < P; ++ph) {
+            float go[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) go[k] = gp[M::koff(k) * PER + ph * P] * g.inv_count;
+            for (int iy = 0; iy < g.gh; ++iy) {
+              const Tap ty = make_tap(g.sh, g.bh, ph, iy, g.gh, H, 0);
+              if (ty.wl == 0.f && ty.wh == 0.f) continue;
+              for (int ix = 0; ix < g.gw; ++ix) {
+                const Tap tx = make_tap(g.sw, g.bw, p, ix, g.gw, W, 0);
+                if (tx.wl == 0.f && tx.wh == 0.f) continue;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                  if (!ctx.act[k]) continue;
+                  float* b = ctx.gimg + (size_t)M::koff(k) * HW;
+                  pr_red_global(b + ty.lo * W + tx.lo, go[k] * ty.wl * tx.wl);
+                  pr_red_global(b + ty.lo * W + tx.hi, go[k] * ty.wl * tx.wh);
+                  pr_red_global(b + ty.hi * W + tx.lo, go[k] * ty.wh * tx.wl);
+                  pr_red_global(b + ty.hi * W + tx.hi, go[k] * ty.wh * tx.wh);
+                }
+              }
+            }
+          }
+        }
+      }
+      // the tile is consumed: fetch the next RoI's (its block has certainly landed by now)
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (inext < nroi && lane == 0) {
+        const int roi = reinterpret_cast<const PrHdr*>(wbuf + (buf ^ 1) * kPrBlockFloats)->roi;
+        pr_bulk_load(tile, gout + ((size_t)roi * C + cbase) * PER, tile_bytes, bar);
+      }
+      i = inext;
+      buf ^= 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int g_roi_pr = 1;         // tuning knob "roi_pr": bit 0 forward, bit 1 backward
+int g_roi_pr = 1;         // tuning knob "roi_pr": bit 0 forward (default), bit 1 backward (experimental: 5.4 ms vs 2.4 ms)
 int g_roi_pr_chunk = 0;   // tuning knob "roi_pr_chunk": RoIs per unit (0: automatic)
 int g_roi_pr_dbg = 0;     // diagnostic knob "roi_pr_dbg": 1 no stores, 2 skip multi-sample RoIs, 4 skip single-sample RoIs
 int g_roi_pr_cpl = 0;     // tuning knob "roi_pr_cpl": channel passes per lane (0: as many as fit, <= 8)
@@ -775,6 +1160,62 @@ int roi_align_fwd_pr(const float* in, const float* rois, float* out, int N, int 
   if (g.CPL == 2) CDDMSL_PR_FWD(7, 2);
   CDDMSL_PR_FWD(7, 1);
 #undef CDDMSL_PR_FWD
+}
+
+static bool pr_geometry_bwd(int C, int H, int W, PrGeom* out) {
+  (void)H;
+  (void)W;
+  const long long per_warp = 2LL * kPrBlockBytes + (kPrTblFloats + kPrTblV + kPrScratch) * 4LL;
+  for (int cpl : {4, 2, 1}) {
+    if (g_roi_pr_cpl && cpl > g_roi_pr_cpl) continue;
+    if (cpl > 1 && 2 * (cpl / 2) >= C) continue;
+    const int ch = 2 * cpl;
+    const long long smem = 256 + kPrBwdWarps * (per_warp + ((ch * 196 + 31) / 32 * 32) * 4LL);
+    if (smem > pr_smem_budget()) continue;
+    out->RS = W;
+    out->PS = 0;
+    out->CPL = cpl;
+    out->CH = ch;
+    out->smem = (int)smem;
+    return true;
+  }
+  return false;
+}
+
+bool roi_pr_bwd_eligible(int N, int C, int H, int W, int R, int P) {
+  PrGeom g;
+  if (!(g_roi_pr & 2) || N <= 0 || R <= 0 || P != 14) return false;
+  if ((long long)R * C * P * P >= (1LL << 40) || (long long)R >= (1LL << 31) - 1) return false;
+  return pr_geometry_bwd(C, H, W, &g);
+}
+
+template <int CPL>
+static int pr_launch_bwd(const float* gout, const float* rois, float* gin, const PrPlan& plan, const PrGeom& g, int N,
+                         int C, int H, int W, int ngroups, int grid, float scale, int sampling_ratio, int aligned,
+                         cudaStream_t stream) {
+  auto k = roi_align_bwd_pr_kernel<CPL>;
+  CDDMSL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
+  k<<<grid, kPrBwdThreads, g.smem, stream>>>(gout, rois, gin, plan, N, C, H, W, ngroups, scale, sampling_ratio,
+                                             aligned, g_roi_pr_dbg);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int roi_align_bwd_pr(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream) {
+  PrGeom g;
+  if (P != 14 || !pr_geometry_bwd(C, H, W, &g)) return CDDMSL_EINVAL;
+  const PrPlan plan = pr_carve(ws, N, R);
+  const int ngroups = ceil_div(C, g.CH);
+  const int chunk = pr_chunk_size(R, ngroups);
+  CDDMSL_CUDA(cudaMemsetAsync(gin, 0, (size_t)N * C * H * W * sizeof(float), stream));
+  int rc = pr_build_plan(plan, rois, N, H, W, R, P, scale, sampling_ratio, aligned, chunk, stream);
+  if (rc) return rc;
+  const long long max_units = ((long long)N + R / chunk + 1) * ngroups;
+  const int grid = (int)min((long long)sm_count(), max_units);
+  if (g.CPL == 4) return pr_launch_bwd<4>(gout, rois, gin, plan, g, N, C, H, W, ngroups, grid, scale, sampling_ratio, aligned, stream);
+  if (g.CPL == 2) return pr_launch_bwd<2>(gout, rois, gin, plan, g, N, C, H, W, ngroups, grid, scale, sampling_ratio, aligned, stream);
+  return pr_launch_bwd<1>(gout, rois, gin, plan, g, N, C, H, W, ngroups, grid, scale, sampling_ratio, aligned, stream);
 }
 
 int tune_roi_pr(const char* key, int value) {
