@@ -391,3 +391,74 @@ extern "C" int cddmsl_align_loss(const float* packed_all, const float* norms_loc
   CDDMSL_CHECK_LAUNCH();
   return CDDMSL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// KD regulariser of the image-level branch (detectron2/modeling/meta_arch/rcnn.py:265-272):
+// kd = L1Loss()(teacher.detach(), student) = mean |teacher - student| over all elements; the gradient
+// d kd / d student = sign(student - teacher) / numel comes out of the same pass.  Deterministic: fixed-order
+// per-block partial sums, summed in order by the last block.
+// ------------------------------------------------------------------------------------------------
+namespace cddmsl {
+constexpr int kKdThreads = 256, kKdMaxBlocks = 1024;
+
+__global__ void __launch_bounds__(kKdThreads) kd_l1_kernel(const float* __restrict__ teacher,
+                                                          const float* __restrict__ student, long long n, float inv_n,
+                                                          const float* __restrict__ grad_scale, float* __restrict__ loss,
+                                                          float* __restrict__ dstudent, float* __restrict__ partial,
+                                                          unsigned int* __restrict__ ticket) {
+  __shared__ float red[kKdThreads / 32];
+  __shared__ bool last;
+  const float gs = grad_scale ? __ldg(grad_scale) * inv_n : inv_n;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * kKdThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kKdThreads) {
+    const float d = __ldg(student + i) - __ldg(teacher + i);
+    acc += fabsf(d);
+    // torch's L1 backward: sign(input - target) * grad / numel, sign(0) = 0
+    if (dstudent) dstudent[i] = d > 0.f ? gs : d < 0.f ? -gs : 0.f;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kKdThreads / 32; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += *((volatile float*)partial + b);
+    *loss = t * inv_n;
+    *ticket = 0u;  // workspace is reusable without another memset
+  }
+}
+}  // namespace cddmsl
+
+extern "C" size_t cddmsl_kd_l1_loss_workspace_bytes(void) { return (cddmsl::kKdMaxBlocks + 64) * sizeof(float); }
+
+extern "C" int cddmsl_kd_l1_loss(const float* teacher, const float* student, int64_t numel, const float* grad_scale,
+                                 float* loss, float* dstudent, void* workspace, size_t workspace_bytes,
+                                 cddmsl_stream_t stream_) {
+  using namespace cddmsl;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (numel < 0 || !loss) return CDDMSL_EINVAL;
+  if (numel == 0) {  // mean over nothing: NaN like torch's L1Loss on empty inputs
+    const float nanv = __builtin_nanf("");
+    CDDMSL_CUDA(cudaMemcpyAsync(loss, &nanv, sizeof(float), cudaMemcpyHostToDevice, stream));
+    return CDDMSL_OK;
+  }
+  if (!teacher || !student || !workspace) return CDDMSL_EINVAL;
+  if (workspace_bytes < cddmsl_kd_l1_loss_workspace_bytes()) return CDDMSL_EWORKSPACE;
+  float* partial = (float*)workspace;
+  unsigned int* ticket = (unsigned int*)(partial + kKdMaxBlocks);
+  CDDMSL_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
+  long long blocks = (numel + kKdThreads - 1) / kKdThreads;
+  if (blocks > kKdMaxBlocks) blocks = kKdMaxBlocks;
+  kd_l1_kernel<<<(unsigned)blocks, kKdThreads, 0, stream>>>(teacher, student, (long long)numel, 1.0f / (float)numel,
+                                                            grad_scale, loss, dstudent, partial, ticket);
+  count_launch();
+  return (int)cudaGetLastError();
+}

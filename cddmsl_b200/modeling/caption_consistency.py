@@ -66,3 +66,11 @@ def image_caption_consistency_loss(trgt: torch.Tensor, src: torch.Tensor,
     """rcnn.py:305-317 (`v2l_contrastive` tail): same loss with the operands in the reference's order,
     `joint = trgt @ src.T` (the loss is symmetric in the pair, gradients follow the operands)."""
     return caption_consistency_loss(trgt, src, group)
+
+
+def kd_l1_loss(teacher: torch.Tensor, student: torch.Tensor) -> torch.Tensor:
+    """KD regulariser of the image-level branch, rcnn.py:265-272: `L1Loss()(v2l(offline_backbone(src)).detach(),
+    v2l(backbone(src)))` on the [B, 768] V2L features.  One kernel yields the loss and the student's gradient;
+    the teacher never receives one."""
+    loss, _ = ops.kd_l1(teacher.detach(), student, bool(student.requires_grad and torch.is_grad_enabled()))
+    return loss

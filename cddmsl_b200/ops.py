@@ -415,3 +415,44 @@ def _(packed_all, norms_local, rank, grad_scale, want_grads):
     world, _, n_local, d = packed_all.shape
     shape = (n_local, d) if want_grads else (0,)
     return packed_all.new_empty(()), packed_all.new_empty(shape), packed_all.new_empty(shape)
+
+
+# ------------------------------------------------------------------------------------------ KD regulariser
+@torch.library.custom_op("cddmsl_b200::kd_l1", mutates_args=(), device_types="cuda")
+def kd_l1(teacher: Tensor, student: Tensor, want_grad: bool) -> Tuple[Tensor, Tensor]:
+    """rcnn.py:265-272: mean |teacher - student| and, from the same pass, d loss / d student (unit upstream scale)."""
+    _lib.require_cuda(student, "student")
+    _lib.require_cuda(teacher, "teacher")
+    assert teacher.shape == student.shape, "L1Loss: teacher and student features must have the same shape"
+    t, s = _f32c(teacher), _f32c(student)
+    dev = s.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ds = torch.empty_like(s) if want_grad else torch.empty((0,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_kd_l1_loss_workspace_bytes(), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.cddmsl_kd_l1_loss(_lib.ptr(t), _lib.ptr(s), s.numel(), None, _lib.ptr(loss),
+                                       _lib.ptr(ds) if want_grad else None, _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr(dev)), "kd_l1_loss")
+    return loss, ds
+
+
+@kd_l1.register_fake
+def _(teacher, student, want_grad):
+    return student.new_empty(()), (torch.empty_like(student) if want_grad else student.new_empty((0,)))
+
+
+def _kd_setup(ctx, inputs, output):
+    ctx.have = inputs[2]
+    if inputs[2]:
+        ctx.save_for_backward(output[1])
+
+
+def _kd_bwd(ctx, gloss, _gds):
+    if not ctx.have:
+        raise RuntimeError("kd_l1: backward without a recorded gradient")
+    (ds,) = ctx.saved_tensors
+    return None, ds * gloss, None   # the teacher is detached (rcnn.py:268)
+
+
+kd_l1.register_autograd(_kd_bwd, setup_context=_kd_setup)

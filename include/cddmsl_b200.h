@@ -150,6 +150,14 @@ int cddmsl_align_loss(const float* packed_all, const float* norms_local, int wor
                       const float* grad_scale, float* loss, float* da, float* db, void* workspace,
                       size_t workspace_bytes, cddmsl_stream_t stream);
 
+/* KD regulariser of the image-level branch, detectron2/modeling/meta_arch/rcnn.py:265-272:
+ * loss = L1Loss()(teacher.detach(), student) = mean |teacher - student| over `numel` elements ([B,768] V2L
+ * features); dstudent (nullable, [numel]) = sign(student - teacher) * scale / numel with scale = *grad_scale
+ * (device pointer, NULL = 1) -- the gradient autograd would produce, from the same pass.  Deterministic. */
+size_t cddmsl_kd_l1_loss_workspace_bytes(void);
+int cddmsl_kd_l1_loss(const float* teacher, const float* student, int64_t numel, const float* grad_scale, float* loss,
+                      float* dstudent, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

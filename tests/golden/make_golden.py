@@ -21,6 +21,17 @@ What it records (all seeded, fp32 / int64):
     (`detectron2/structures/boxes.py`), both loaded verbatim with two import stubs: ROI-head and RPN settings,
     an image without ground truth, duplicate gt boxes (argmax ties), degenerate proposals.
 
+  * head_ref.npz — the reference's own `FastRCNNOutputLayers` (`detectron2/modeling/roi_heads/fast_rcnn.py`, loaded
+    verbatim by file path with its package imports stubbed: fvcore.nn, detectron2.config.configurable (identity),
+    detectron2.layers (ShapeSpec / cat / cross_entropy / nonzero_tuple from `layers/wrappers.py`), soft_nms,
+    box_regression (the reference's own file), structures, utils.events (a recording storage)): `forward`,
+    `focal_loss`, CE and weighted CE through `losses`, `_log_classification_stats`, gradients by autograd; zero and
+    learned background row, one saturated row.  THIS pins pieces 3 (head) to the reference itself.
+  * align_ref.npz — the literal source lines `detectron2/modeling/meta_arch/rcnn.py:455-470` (region level),
+    `:305-319` (image level) and `:270-272` (KD L1), read from the file at generation time and executed on seeded
+    tensors (single process with an identity gather, and under a real 2-process gloo group with the reference's
+    `GatherLayer`).  THIS pins piece 4 to the reference itself.
+
 The tests never read /root/reference; they read these files.
 """
 import importlib.util
@@ -297,10 +308,201 @@ def match_cases():
     print("match:", g_len, m_len)
 
 
+class _RecordingStorage:
+    def __init__(self):
+        self.scalars = {}
+
+    def put_scalar(self, name, value, **kw):
+        self.scalars[name] = float(value)
+
+
+def _load_ref_fast_rcnn(storage):
+    """detectron2/modeling/roi_heads/fast_rcnn.py, verbatim, with its package imports stubbed."""
+    import collections
+    import types
+
+    wr = _load_with_stubs("ref_wrappers", "detectron2/layers/wrappers.py", {})
+    br = _load_with_stubs("ref_box_regression2", "detectron2/modeling/box_regression.py", {
+        "fvcore": {}, "fvcore.nn": {"giou_loss": None, "smooth_l1_loss": None}, "detectron2": {},
+        "detectron2.layers": {"cat": torch.cat}, "detectron2.structures": {"Boxes": object}})
+    ShapeSpec = collections.namedtuple("ShapeSpec", ["channels", "height", "width", "stride"],
+                                       defaults=(None, None, None, None))
+
+    def configurable(f=None, **kw):   # @configurable with explicit keyword arguments == the plain constructor
+        return f
+
+    def smooth_l1_loss(inp, tgt, beta, reduction="none"):   # fvcore's published definition
+        n = torch.abs(inp - tgt)
+        loss = n if beta < 1e-5 else torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
+        return loss.sum() if reduction == "sum" else loss.mean() if reduction == "mean" else loss
+
+    stubs = {
+        "fvcore": {}, "fvcore.nn": {"giou_loss": None, "smooth_l1_loss": smooth_l1_loss},
+        "detectron2": {}, "detectron2.config": {"configurable": configurable},
+        "detectron2.layers": {"ShapeSpec": ShapeSpec, "batched_nms": None, "cat": wr.cat,
+                              "cross_entropy": wr.cross_entropy, "nonzero_tuple": wr.nonzero_tuple},
+        "detectron2.layers.soft_nms": {"batched_soft_nms": None},
+        "detectron2.modeling": {}, "detectron2.modeling.box_regression": {"Box2BoxTransform": br.Box2BoxTransform},
+        "detectron2.structures": {"Boxes": object, "Instances": object},
+        "detectron2.utils": {}, "detectron2.utils.events": {"get_event_storage": lambda: storage},
+    }
+    return _load_with_stubs("ref_fast_rcnn", "detectron2/modeling/roi_heads/fast_rcnn.py", stubs), br, ShapeSpec
+
+
+class _Props:   # the two fields `losses` reads from a proposal `Instances`
+    def __init__(self, boxes, gt):
+        self.proposal_boxes = type("B", (), {"tensor": boxes})()
+        self.gt_classes = gt
+
+    def has(self, name):
+        return False
+
+
+def head_ref_cases():
+    import tempfile
+
+    storage = _RecordingStorage()
+    ref, br, ShapeSpec = _load_ref_fast_rcnn(storage)
+    g = synth.generator(23)
+    cfg = synth.CONFIGS["tiny"]
+    r, k, d_emb = 80, cfg.num_classes, cfg.emb_dim
+    x, w, w_bg, gt = synth.make_head_inputs(cfg, g, n_rois=r)
+    x[5] = 6.0 * w[int(gt[5]) if int(gt[5]) < k else 0]      # one saturated row (softmax p_t == 1 in fp32)
+    gt[5] = gt[5] if int(gt[5]) < k else 0
+    w_bg2 = torch.randn(1, d_emb, generator=g) * 0.1
+    boxes = synth.make_boxes(r, 600, 1000, g, degenerate_frac=0.0)
+    out = dict(x=x.numpy(), w=w.numpy(), gt=gt.numpy(), w_bg2=w_bg2.numpy(),
+               params=np.array([cfg.temperature, cfg.focal_gamma, cfg.bg_weight], dtype=np.float64))
+    with tempfile.TemporaryDirectory() as td:
+        emb = os.path.join(td, "emb.pth")
+        torch.save(w.clone(), emb)
+        for mode, focal, bgw in (("focal", cfg.focal_gamma, cfg.bg_weight), ("ce", None, None),
+                                 ("wce", None, cfg.bg_weight)):
+            for tag, wb in (("zero_bg", None), ("learned_bg", w_bg2)):
+                head = ref.FastRCNNOutputLayers(
+                    ShapeSpec(channels=d_emb), box2box_transform=br.Box2BoxTransform(weights=(10.0, 10.0, 5.0, 5.0)),
+                    num_classes=k, clip_cls_emb=(True, emb, "CLIPRes5ROIHeads", d_emb), bg_cls_loss_weight=bgw,
+                    openset_test=(None, None, cfg.temperature, focal))
+                head.train()
+                if wb is not None:
+                    with torch.no_grad():
+                        head.cls_bg_score.weight.copy_(wb)
+                xx = x.clone().requires_grad_(True)
+                scores, deltas = head(xx)                                       # fast_rcnn.py:529-572
+                storage.scalars.clear()
+                losses = head.losses((scores, deltas.detach()), [_Props(boxes, gt)])   # :574-622 (+ :624-644, :100-127)
+                loss = losses["loss_cls"]
+                loss.backward()
+                key = f"{mode}_{tag}"
+                out[f"scores_{tag}"] = scores.detach().numpy()
+                out[f"loss_{key}"] = loss.detach().numpy()
+                out[f"dx_{key}"] = xx.grad.numpy()            # NaN in the saturated row for the focal loss (:630-633)
+                out[f"stats_{tag}"] = np.array([storage.scalars.get("fast_rcnn/cls_accuracy", -1.0),
+                                                storage.scalars.get("fast_rcnn/fg_cls_accuracy", -1.0),
+                                                storage.scalars.get("fast_rcnn/false_negative", -1.0)])
+    np.savez_compressed(os.path.join(HERE, "head_ref.npz"), **out)
+    print("head_ref:", sorted(k for k in out if k.startswith("loss_")))
+
+
+def _ref_lines(rel, first, last):
+    with open(os.path.join(REF, rel)) as fh:
+        lines = fh.read().splitlines()[first - 1:last]
+    import textwrap
+    return textwrap.dedent("\n".join(lines))
+
+
+def _ref_align_fns():
+    """The literal alignment-loss source of detectron2/modeling/meta_arch/rcnn.py wrapped into functions."""
+    import textwrap
+
+    from torch import nn
+    region = "def region(self, src_features, target_features, GatherLayer):\n" + textwrap.indent(
+        _ref_lines("detectron2/modeling/meta_arch/rcnn.py", 455, 470), "    ")
+    image = "def image(self, student_features_trgt, student_features_src, kd_loss, GatherLayer):\n" + textwrap.indent(
+        _ref_lines("detectron2/modeling/meta_arch/rcnn.py", 305, 319), "    ")
+    kd = "def kd(teacher_features, student_features_src):\n" + textwrap.indent(
+        _ref_lines("detectron2/modeling/meta_arch/rcnn.py", 270, 272), "    ") + "\n    return kd_loss\n"
+    ns = {"torch": torch, "nn": nn}
+    for src in (region, image, kd):
+        exec(src, ns)
+    return ns["region"], ns["image"], ns["kd"]
+
+
+class _Self:
+    device = torch.device("cpu")
+
+
+class _IdentityGather:
+    @staticmethod
+    def apply(x):
+        return (x,)
+
+
+def _align_ref_worker(rank, world, a_locals, b_locals, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = "29593"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gl = load_by_path("ref_gather", "detectron2/modeling/backbone/clipcap/gather.py")
+    region, image, _ = _ref_align_fns()
+    res = []
+    for fn, extra in ((region, ()), (image, (None,))):
+        a = a_locals[rank].clone().requires_grad_(True)
+        b = b_locals[rank].clone().requires_grad_(True)
+        loss = fn(_Self(), a, b, *extra, gl.GatherLayer)
+        loss = loss[0] if isinstance(loss, tuple) else loss
+        loss.backward()
+        res.append((loss.detach().numpy(), a.grad.numpy(), b.grad.numpy()))
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def align_ref_cases():
+    import torch.multiprocessing as mp
+
+    region, image, kd = _ref_align_fns()
+    g = synth.generator(24)
+    d = {}
+    for tag, (n, dim) in {"n16": (16, 256), "n48": (48, 96), "n256": (256, 256)}.items():
+        a, b = torch.randn(n, dim, generator=g), torch.randn(n, dim, generator=g)
+        for kind, fn, extra in (("region", region, ()), ("image", image, (None,))):
+            aa, bb = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            loss = fn(_Self(), aa, bb, *extra, _IdentityGather)
+            loss = loss[0] if isinstance(loss, tuple) else loss
+            loss.backward()
+            d.update({f"a_{tag}": a.numpy(), f"b_{tag}": b.numpy(), f"{kind}_loss_{tag}": loss.detach().numpy(),
+                      f"{kind}_da_{tag}": aa.grad.numpy(), f"{kind}_db_{tag}": bb.grad.numpy()})
+    # KD regulariser (rcnn.py:265-272): L1 between the frozen teacher's and the student's V2L features [B, 768]
+    t, s_ = torch.randn(8, 768, generator=g), torch.randn(8, 768, generator=g)
+    ss = s_.clone().requires_grad_(True)
+    kl = kd(t, ss)
+    kl.backward()
+    d.update(kd_teacher=t.numpy(), kd_student=s_.numpy(), kd_loss=kl.detach().numpy(), kd_dstudent=ss.grad.numpy())
+    # two ranks, the reference's own GatherLayer
+    world, n_l, dim = 2, 10, 64
+    a_locals = [torch.randn(n_l, dim, generator=g) for _ in range(world)]
+    b_locals = [torch.randn(n_l, dim, generator=g) for _ in range(world)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_align_ref_worker, args=(r, world, a_locals, b_locals, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=180) for _ in range(world))
+    [p.join() for p in procs]
+    for r in range(world):
+        d.update({f"w2_a{r}": a_locals[r].numpy(), f"w2_b{r}": b_locals[r].numpy()})
+        for ki, kind in enumerate(("region", "image")):
+            d.update({f"w2_{kind}_loss": res[r][ki][0], f"w2_{kind}_da{r}": res[r][ki][1],
+                      f"w2_{kind}_db{r}": res[r][ki][2]})
+    np.savez_compressed(os.path.join(HERE, "align_ref.npz"), **d)
+    print("align_ref: region/image single + world2, kd")
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
-    if len(sys.argv) > 1 and sys.argv[1] in ("box_reg", "match"):
-        {"box_reg": box_reg_cases, "match": match_cases}[sys.argv[1]]()
+    if len(sys.argv) > 1 and sys.argv[1] in ("box_reg", "match", "head_ref", "align_ref"):
+        {"box_reg": box_reg_cases, "match": match_cases, "head_ref": head_ref_cases,
+         "align_ref": align_ref_cases}[sys.argv[1]]()
         sys.exit(0)
     roi_cases()
     nms_cases()
@@ -308,5 +510,7 @@ if __name__ == "__main__":
     align_cases()
     box_reg_cases()
     match_cases()
+    head_ref_cases()
+    align_ref_cases()
     sizes = {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")}
     print(sizes, sum(sizes.values()))

@@ -36,6 +36,46 @@ def test_single_rank_fixtures(golden_dir):
         _close(t.grad.cpu().numpy(), a[f"db_{tag}"], 1e-4, "db")
 
 
+def test_reference_rcnn_lines_fixture(golden_dir):
+    """align_ref.npz: the literal lines rcnn.py:455-470 (region), :305-319 (image) and :270-272 (KD) executed on
+    seeded tensors, single process and with the reference's GatherLayer under a 2-rank gloo group."""
+    from cddmsl_b200.modeling import caption_consistency_loss, image_caption_consistency_loss, kd_l1_loss
+
+    a = np.load(os.path.join(golden_dir, "align_ref.npz"))
+    for tag in ("n16", "n48", "n256"):
+        for kind, fn in (("region", caption_consistency_loss), ("image", image_caption_consistency_loss)):
+            s = torch.from_numpy(a[f"a_{tag}"]).to(DEV).requires_grad_(True)
+            t = torch.from_numpy(a[f"b_{tag}"]).to(DEV).requires_grad_(True)
+            loss = fn(s, t)
+            loss.backward()
+            _close(loss.item(), a[f"{kind}_loss_{tag}"], 1e-5, f"{kind} loss")
+            _close(s.grad.cpu().numpy(), a[f"{kind}_da_{tag}"], 1e-4, f"{kind} da")
+            _close(t.grad.cpu().numpy(), a[f"{kind}_db_{tag}"], 1e-4, f"{kind} db")
+    al = [torch.from_numpy(a["w2_a0"]), torch.from_numpy(a["w2_a1"])]
+    bl = [torch.from_numpy(a["w2_b0"]), torch.from_numpy(a["w2_b1"])]
+    for r in range(2):
+        loss, da, db = _emulated_rank(al, bl, r)
+        for kind in ("region", "image"):
+            _close(loss.item(), a[f"w2_{kind}_loss"], 1e-5, "w2 loss")
+            _close(da.cpu().numpy(), a[f"w2_{kind}_da{r}"], 1e-4, "w2 da")
+            _close(db.cpu().numpy(), a[f"w2_{kind}_db{r}"], 1e-4, "w2 db")
+    # KD regulariser: loss within 1e-5, gradient bit-exact (sign / numel)
+    t = torch.from_numpy(a["kd_teacher"]).to(DEV)
+    s = torch.from_numpy(a["kd_student"]).to(DEV).requires_grad_(True)
+    kl = kd_l1_loss(t, s)
+    (kl * 1.0).backward()
+    _close(kl.item(), a["kd_loss"], 1e-5, "kd loss")
+    assert np.array_equal(s.grad.cpu().numpy(), a["kd_dstudent"])
+    s2 = torch.from_numpy(a["kd_student"]).to(DEV).requires_grad_(True)
+    (kd_l1_loss(t, s2) * 0.25).backward()
+    assert np.array_equal(s2.grad.cpu().numpy(), a["kd_dstudent"] * np.float32(0.25))
+    with torch.no_grad():
+        _close(kd_l1_loss(t, s).item(), a["kd_loss"], 1e-5, "kd loss (no grad)")
+    big = torch.randn(70000, 7, device=DEV)   # more elements than one grid pass
+    ref = (big - big.roll(1, 0)).abs().double().mean().item()
+    _close(kd_l1_loss(big.roll(1, 0), big).item(), ref, 1e-5, "kd loss, grid-stride")
+
+
 def test_upstream_gradient_scale_is_applied():
     from cddmsl_b200.modeling import caption_consistency_loss, image_caption_consistency_loss
 

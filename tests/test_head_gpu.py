@@ -69,6 +69,44 @@ def test_fixture_tiny_all_modes(golden_dir):
             _close(got[~nan_rows], want[~nan_rows], 1e-4, f"dx {mode}{tag}")
 
 
+def test_reference_fast_rcnn_fixture_all_modes(golden_dir):
+    """head_ref.npz: outputs of the reference's OWN FastRCNNOutputLayers.forward / losses / focal_loss /
+    _log_classification_stats (fast_rcnn.py loaded verbatim, tests/golden/make_golden.py:head_ref_cases)."""
+    from cddmsl_b200.modeling import fast_rcnn as fr
+
+    d = np.load(os.path.join(golden_dir, "head_ref.npz"))
+    T, gamma, bgw = (float(v) for v in d["params"])
+    x, w, gt = torch.from_numpy(d["x"]), torch.from_numpy(d["w"]), torch.from_numpy(d["gt"])
+    k, dim = w.shape
+    for tag, wb in (("zero_bg", None), ("learned_bg", torch.from_numpy(d["w_bg2"]))):
+        for mode, (gam, bw) in {"focal": (gamma, bgw), "ce": (None, None), "wce": (None, bgw)}.items():
+            m = _predictor(k, dim, w, wb, gamma=gam, bgw=bw, temperature=T, strict=True)
+            xx = x.to(DEV).requires_grad_(True)
+            seen = {}
+            fr.set_scalar_sink(lambda kk, v: seen.__setitem__(kk, v))
+            try:
+                preds = m(xx)
+                losses = m.losses(preds, _proposals(gt))
+            finally:
+                fr.set_scalar_sink(None)
+            losses["loss_cls"].backward()
+            _close(preds[0].detach().cpu().numpy(), d[f"scores_{tag}"], 1e-5, "scores")
+            _close(losses["loss_cls"].item(), d[f"loss_{mode}_{tag}"], 1e-5, f"loss {mode} {tag}")
+            want = d[f"dx_{mode}_{tag}"]
+            got = xx.grad.cpu().numpy()
+            nan_rows = np.isnan(want).any(axis=1)
+            assert np.array_equal(np.isnan(got).any(axis=1), nan_rows), "strict mode reproduces the reference's NaN rows"
+            _close(got[~nan_rows], want[~nan_rows], 1e-4, f"dx {mode} {tag}")
+            # per-element relative check where the value is not tiny (DESIGN.md section 2, tolerance note)
+            big = np.abs(want) > 1e-2 * np.abs(want[~nan_rows]).max()
+            big &= ~nan_rows[:, None]
+            assert (np.abs(got[big] - want[big]) <= 1e-4 * np.abs(want[big])).all()
+            acc, fgacc, fn = d[f"stats_{tag}"]
+            assert abs(seen["fast_rcnn/cls_accuracy"] - acc) < 1e-12
+            assert abs(seen["fast_rcnn/fg_cls_accuracy"] - fgacc) < 1e-12
+            assert abs(seen["fast_rcnn/false_negative"] - fn) < 1e-12
+
+
 def test_saturated_row_default_is_analytic_limit(golden_dir):
     d = np.load(os.path.join(golden_dir, "head_tiny.npz"))
     T, gamma, bgw = (float(v) for v in d["params"])

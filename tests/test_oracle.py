@@ -152,6 +152,58 @@ def test_head_and_align_fixtures_reproduce(golden_dir):
         assert np.allclose(loss.item(), a[f"loss_{tag}"], rtol=1e-6)
 
 
+def test_oracle_head_equals_reference_fast_rcnn(golden_dir):
+    """head_ref.npz was produced by the reference's OWN FastRCNNOutputLayers (fast_rcnn.py loaded verbatim by
+    tests/golden/make_golden.py:head_ref_cases): forward :529-572, losses :574-622, focal_loss :624-644,
+    _log_classification_stats :100-127.  The restatement in oracle/torch_ref.py must reproduce it."""
+    d = np.load(os.path.join(golden_dir, "head_ref.npz"))
+    T, gamma, bgw = (float(v) for v in d["params"])
+    x, w, gt = torch.from_numpy(d["x"]), torch.from_numpy(d["w"]), torch.from_numpy(d["gt"])
+    k = w.shape[0]
+    for tag, wb in (("zero_bg", torch.zeros(1, x.shape[1])), ("learned_bg", torch.from_numpy(d["w_bg2"]))):
+        for mode, (gam, bw) in {"focal": (gamma, bgw), "ce": (None, None), "wce": (None, bgw)}.items():
+            xx = x.clone().requires_grad_(True)
+            s = torch_ref.clip_head_scores(xx, w, wb, T)
+            loss = torch_ref.cls_loss(s, gt, k, gam, bw)
+            loss.backward()
+            assert np.array_equal(s.detach().numpy(), d[f"scores_{tag}"]), "logits are bit-equal to the reference"
+            assert np.allclose(loss.item(), d[f"loss_{mode}_{tag}"], rtol=1e-6, atol=0)
+            assert np.allclose(xx.grad.numpy(), d[f"dx_{mode}_{tag}"], rtol=1e-5, atol=1e-7, equal_nan=True)
+        acc, nfg, fgacc, fn = torch_ref.classification_stats(s.detach(), gt)
+        want = d[f"stats_{tag}"]
+        assert np.allclose([acc / len(gt), fgacc / nfg, fn / nfg], want, rtol=0, atol=1e-12)
+    assert np.isnan(d["dx_focal_zero_bg"]).any(), "the fixture keeps the reference's NaN row at softmax saturation"
+
+
+def test_oracle_alignment_equals_reference_rcnn_lines(golden_dir):
+    """align_ref.npz was produced by executing the literal lines rcnn.py:455-470 / :305-319 / :270-272 (read from
+    the reference file at generation time), single-process and under a 2-rank gloo group with the reference's own
+    GatherLayer."""
+    a = np.load(os.path.join(golden_dir, "align_ref.npz"))
+    for tag in ("n16", "n48", "n256"):
+        for kind in ("region", "image"):
+            x, y = torch.from_numpy(a[f"a_{tag}"]), torch.from_numpy(a[f"b_{tag}"])
+            xx, yy = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            # region level: S = src @ tgt^T with (src, tgt) = (a, b); image level: S = trgt @ src^T with (trgt, src) = (a, b)
+            loss = torch_ref.caption_consistency_loss(xx, yy)
+            loss.backward()
+            assert np.allclose(loss.item(), a[f"{kind}_loss_{tag}"], rtol=1e-6, atol=0)
+            assert np.allclose(xx.grad.numpy(), a[f"{kind}_da_{tag}"], rtol=1e-5, atol=1e-8)
+            assert np.allclose(yy.grad.numpy(), a[f"{kind}_db_{tag}"], rtol=1e-5, atol=1e-8)
+    t, s_ = torch.from_numpy(a["kd_teacher"]), torch.from_numpy(a["kd_student"]).requires_grad_(True)
+    kl = torch_ref.kd_l1_loss(t, s_)
+    kl.backward()
+    assert np.allclose(kl.item(), a["kd_loss"], rtol=1e-6) and np.array_equal(s_.grad.numpy(), a["kd_dstudent"])
+    al = [torch.from_numpy(a["w2_a0"]), torch.from_numpy(a["w2_a1"])]
+    bl = [torch.from_numpy(a["w2_b0"]), torch.from_numpy(a["w2_b1"])]
+    loss, ga, gb = torch_ref.caption_consistency_world(al, bl)
+    for kind in ("region", "image"):
+        assert np.allclose(loss.item(), a[f"w2_{kind}_loss"], rtol=1e-6)
+        for r in range(2):
+            assert np.allclose(ga[r].numpy(), a[f"w2_{kind}_da{r}"], rtol=1e-5, atol=1e-8)
+            assert np.allclose(gb[r].numpy(), a[f"w2_{kind}_db{r}"], rtol=1e-5, atol=1e-8)
+
+
 def test_world_emulation_matches_real_gatherlayer_fixture(golden_dir):
     w = np.load(os.path.join(golden_dir, "align_world2.npz"))
     a = [torch.from_numpy(w["a0"]), torch.from_numpy(w["a1"])]
