@@ -27,6 +27,8 @@ SIGNATURES = {
     "cddmsl_roi_align_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     "cddmsl_roi_align_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "cddmsl_roi_align_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
+    "cddmsl_roi_align_fwd2": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
+    "cddmsl_roi_align_bwd2": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     "cddmsl_nms_workspace_bytes": (_sz, [_i64]),
     "cddmsl_nms": (_i, [_vp, _vp, _vp, _i64, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "cddmsl_nms_batched_workspace_bytes": (_sz, [_i, _i64]),

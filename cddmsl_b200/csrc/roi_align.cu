@@ -421,7 +421,8 @@ int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int 
 bool roi_pr_eligible(int N, int C, int H, int W, int R, int P, int bit);
 size_t roi_pr_workspace_bytes(int N, int R);
 int roi_align_fwd_pr(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, int P,
-                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
+                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream,
+                     const float* in2 = nullptr, float* out2 = nullptr);
 int roi_align_bwd_pr(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
                      float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
 bool roi_pr_bwd_eligible(int N, int C, int H, int W, int R, int P);
@@ -541,4 +542,34 @@ extern "C" int cddmsl_roi_align_bwd(const float* gout, const float* rois, float*
   count_launch();
   CDDMSL_CHECK_LAUNCH();
   return CDDMSL_OK;
+}
+
+// ---- dual-map variants: the same RoIs on two feature maps of the same shape ---------------------------------------
+extern "C" int cddmsl_roi_align_fwd2(const float* in_a, const float* in_b, const float* rois, float* out_a,
+                                     float* out_b, int N, int C, int H, int W, int R, int PH, int PW,
+                                     float spatial_scale, int sampling_ratio, int aligned, void* workspace,
+                                     size_t workspace_bytes, cddmsl_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool ws_ok = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0;
+  if (N > 0 && C > 0 && H > 0 && W > 0 && R > 0 && PH == PW && in_a && in_b && rois && out_a && out_b && ws_ok &&
+      (reinterpret_cast<uintptr_t>(out_a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_b) & 15) == 0 &&
+      workspace_bytes >= roi_pr_workspace_bytes(N, R) && roi_pr_eligible(N, C, H, W, R, PH, 1))
+    return roi_align_fwd_pr(in_a, rois, out_a, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned, workspace,
+                            stream, in_b, out_b);
+  int rc = cddmsl_roi_align_fwd(in_a, rois, out_a, N, C, H, W, R, PH, PW, spatial_scale, sampling_ratio, aligned,
+                                workspace, workspace_bytes, stream_);
+  if (rc) return rc;
+  return cddmsl_roi_align_fwd(in_b, rois, out_b, N, C, H, W, R, PH, PW, spatial_scale, sampling_ratio, aligned,
+                              workspace, workspace_bytes, stream_);
+}
+
+extern "C" int cddmsl_roi_align_bwd2(const float* gout_a, const float* gout_b, const float* rois, float* gin_a,
+                                     float* gin_b, int N, int C, int H, int W, int R, int PH, int PW,
+                                     float spatial_scale, int sampling_ratio, int aligned, void* workspace,
+                                     size_t workspace_bytes, cddmsl_stream_t stream_) {
+  int rc = cddmsl_roi_align_bwd(gout_a, rois, gin_a, N, C, H, W, R, PH, PW, spatial_scale, sampling_ratio, aligned,
+                                workspace, workspace_bytes, stream_);
+  if (rc) return rc;
+  return cddmsl_roi_align_bwd(gout_b, rois, gin_b, N, C, H, W, R, PH, PW, spatial_scale, sampling_ratio, aligned,
+                              workspace, workspace_bytes, stream_);
 }

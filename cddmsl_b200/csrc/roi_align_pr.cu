@@ -1137,8 +1137,16 @@ static int pr_launch_fwd(const float* in, const float* rois, float* out, const P
   return (int)cudaGetLastError();
 }
 
+// in2 / out2 (nullable): a second feature map of the same shape pooled with the SAME RoIs (the source / target pair
+// of the region-level consistency branch, clip_roi_heads.py:117-132): the plan -- bands, image buckets, chunk list --
+// is built once and serves both launches.
+static int pr_fwd_launch(const float* in, const float* rois, float* out, const PrPlan& plan, const PrGeom& g, int N,
+                         int C, int H, int W, int P, int ngroups, int grid, float scale, int sampling_ratio,
+                         int aligned, cudaStream_t stream);
+
 int roi_align_fwd_pr(const float* in, const float* rois, float* out, int N, int C, int H, int W, int R, int P,
-                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream) {
+                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream,
+                     const float* in2 = nullptr, float* out2 = nullptr) {
   PrGeom g;
   if (!pr_geometry(C, H, W, P, &g)) return CDDMSL_EINVAL;
   const PrPlan plan = pr_carve(ws, N, R);
@@ -1148,6 +1156,15 @@ int roi_align_fwd_pr(const float* in, const float* rois, float* out, int N, int 
   if (rc) return rc;
   const long long max_units = ((long long)N + R / chunk + 1) * ngroups;
   const int grid = (int)min((long long)sm_count(), max_units);
+  rc = pr_fwd_launch(in, rois, out, plan, g, N, C, H, W, P, ngroups, grid, scale, sampling_ratio, aligned, stream);
+  if (rc || !in2) return rc;
+  CDDMSL_CUDA(cudaMemsetAsync(plan.counter, 0, sizeof(int), stream));  // the unit counter; the plan stays
+  return pr_fwd_launch(in2, rois, out2, plan, g, N, C, H, W, P, ngroups, grid, scale, sampling_ratio, aligned, stream);
+}
+
+static int pr_fwd_launch(const float* in, const float* rois, float* out, const PrPlan& plan, const PrGeom& g, int N,
+                         int C, int H, int W, int P, int ngroups, int grid, float scale, int sampling_ratio,
+                         int aligned, cudaStream_t stream) {
 #define CDDMSL_PR_FWD(PV, CV)                                                                                  \
   return pr_launch_fwd<PV, CV>(in, rois, out, plan, g, N, C, H, W, ngroups, grid, scale, sampling_ratio, aligned, \
                                stream)

@@ -57,6 +57,14 @@ class ROIAlign(nn.Module):
         return roi_align(input, rois.to(dtype=input.dtype), self.output_size, self.spatial_scale,
                          self.sampling_ratio, self.aligned)
 
+    def forward_pair(self, input_a, input_b, rois):
+        """The same RoIs on two feature maps of the same shape (source / target of the region-level consistency
+        branch, clip_roi_heads.py:117-132): one planning pass serves both; equals two `forward` calls bit for bit."""
+        assert rois.dim() == 2 and rois.size(1) == 5
+        ph, pw = (self.output_size, self.output_size) if isinstance(self.output_size, int) else self.output_size
+        return ops.roi_align_pair(input_a, input_b, rois.to(dtype=input_a.dtype), float(self.spatial_scale), int(ph),
+                                  int(pw), int(self.sampling_ratio), bool(self.aligned))
+
     def __repr__(self):
         return (f"{self.__class__.__name__}(output_size={self.output_size}, spatial_scale={self.spatial_scale}, "
                 f"sampling_ratio={self.sampling_ratio}, aligned={self.aligned})")

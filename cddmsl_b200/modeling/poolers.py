@@ -65,6 +65,16 @@ class ROIPooler(nn.Module):
         assert canonical_box_size > 0
         self.canonical_box_size = canonical_box_size
 
+    def forward_pair(self, x_a: List[torch.Tensor], x_b: List[torch.Tensor], box_lists):
+        """`forward` on two feature lists with the SAME boxes (clip_roi_heads.py:123-128 pools features_src and
+        features_trgt with identical proposal boxes): a single level shares one planning pass between the maps."""
+        if len(self.level_poolers) != 1 or len(box_lists) == 0 or x_a[0].shape != x_b[0].shape:
+            return self.forward(x_a, box_lists), self.forward(x_b, box_lists)
+        assert isinstance(x_a, list) and isinstance(x_b, list) and isinstance(box_lists, list)
+        assert len(x_a) == 1 and len(x_b) == 1 and len(box_lists) == x_a[0].size(0)
+        rois = convert_boxes_to_pooler_format(box_lists)
+        return self.level_poolers[0].forward_pair(x_a[0], x_b[0], rois)
+
     def forward(self, x: List[torch.Tensor], box_lists) -> torch.Tensor:
         num_level_assignments = len(self.level_poolers)
         assert isinstance(x, list) and isinstance(box_lists, list), "Arguments to pooler must be lists"

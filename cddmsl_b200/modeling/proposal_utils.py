@@ -15,6 +15,12 @@ import torch
 from ..layers import batched_nms, batched_nms_images, cat
 from ..structures import Boxes, Instances
 
+# The container types the results are built with.  When `find_top_rpn_proposals` is patched into the reference's
+# loop, set these to the reference's own classes -- its `add_ground_truth_to_proposals` calls
+# `Instances.cat` / `Boxes.cat` on what this function returns:
+#     pu.CONTAINERS.update(Instances=detectron2.structures.Instances, Boxes=detectron2.structures.Boxes)
+CONTAINERS = {"Instances": Instances, "Boxes": Boxes}
+
 
 BATCHED_IMAGES = True  # False: the upstream-shaped per-image loop (one NMS launch sequence + syncs per image)
 
@@ -49,8 +55,8 @@ def _per_image_batched(topk_proposals, topk_scores, level_ids, image_sizes, nms_
     results: List[Instances] = []
     for n, image_size in enumerate(image_sizes):
         k = keep[n, : min(int(host[n]), post_nms_topk)]
-        res = Instances(image_size)
-        res.proposal_boxes = Boxes(boxes[n][k])
+        res = CONTAINERS["Instances"](image_size)
+        res.proposal_boxes = CONTAINERS["Boxes"](boxes[n][k])
         res.objectness_logits = scores[n][k]
         results.append(res)
     return results
@@ -87,7 +93,7 @@ def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits
                                   min_box_size, training)
     results: List[Instances] = []
     for n, image_size in enumerate(image_sizes):
-        boxes = Boxes(topk_proposals[n])
+        boxes = CONTAINERS["Boxes"](topk_proposals[n])
         scores_per_img = topk_scores[n]
         lvl = level_ids
         valid_mask = torch.isfinite(boxes.tensor).all(dim=1) & torch.isfinite(scores_per_img)
@@ -101,7 +107,7 @@ def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits
             boxes, scores_per_img, lvl = boxes[keep], scores_per_img[keep], lvl[keep]
         keep = batched_nms(boxes.tensor, scores_per_img, lvl, nms_thresh)
         keep = keep[:post_nms_topk]  # already sorted by score
-        res = Instances(image_size)
+        res = CONTAINERS["Instances"](image_size)
         res.proposal_boxes = boxes[keep]
         res.objectness_logits = scores_per_img[keep]
         results.append(res)

@@ -91,6 +91,84 @@ def _roi_align_bwd(ctx, grad):
 roi_align.register_autograd(_roi_align_bwd, setup_context=_roi_align_setup)
 
 
+# ---- the same RoIs on two maps (clip_roi_heads.py:117-132) -------------------------------------------------------
+@torch.library.custom_op("cddmsl_b200::roi_align_pair", mutates_args=(), device_types="cuda")
+def roi_align_pair(input_a: Tensor, input_b: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int,
+                   pooled_width: int, sampling_ratio: int, aligned: bool) -> Tuple[Tensor, Tensor]:
+    _lib.require_cuda(input_a, "input_a")
+    _lib.require_cuda(input_b, "input_b")
+    _lib.require_cuda(rois, "rois")
+    assert input_a.shape == input_b.shape, "roi_align_pair: the two feature maps must have the same shape"
+    xa, xb, r = _f32c(input_a), _f32c(input_b), _f32c(rois)
+    n, c, h, w = xa.shape
+    nr = r.shape[0]
+    oa = torch.empty((nr, c, pooled_height, pooled_width), dtype=torch.float32, device=xa.device)
+    ob = torch.empty_like(oa)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_roi_align_fwd_workspace_bytes(n, c, h, w, nr), xa.device)
+    with torch.cuda.device(xa.device):
+        _lib.check(L.cddmsl_roi_align_fwd2(_lib.ptr(xa), _lib.ptr(xb), _lib.ptr(r), _lib.ptr(oa), _lib.ptr(ob), n, c,
+                                           h, w, nr, pooled_height, pooled_width, spatial_scale, sampling_ratio,
+                                           int(aligned), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(xa.device)),
+                   "roi_align_fwd2")
+    if input_a.dtype != torch.float32:
+        oa, ob = oa.to(input_a.dtype), ob.to(input_a.dtype)
+    return oa, ob
+
+
+@roi_align_pair.register_fake
+def _(input_a, input_b, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio, aligned):
+    shape = (rois.shape[0], input_a.shape[1], pooled_height, pooled_width)
+    return input_a.new_empty(shape), input_a.new_empty(shape)
+
+
+@torch.library.custom_op("cddmsl_b200::roi_align_pair_backward", mutates_args=(), device_types="cuda")
+def roi_align_pair_backward(grad_a: Tensor, grad_b: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int,
+                            pooled_width: int, batch_size: int, channels: int, height: int, width: int,
+                            sampling_ratio: int, aligned: bool) -> Tuple[Tensor, Tensor]:
+    ga, gb, r = _f32c(grad_a), _f32c(grad_b), _f32c(rois)
+    nr = r.shape[0]
+    ia = torch.empty((batch_size, channels, height, width), dtype=torch.float32, device=ga.device)
+    ib = torch.empty_like(ia)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_roi_align_bwd_workspace_bytes(batch_size, channels, height, width, nr), ga.device)
+    with torch.cuda.device(ga.device):
+        _lib.check(L.cddmsl_roi_align_bwd2(_lib.ptr(ga), _lib.ptr(gb), _lib.ptr(r), _lib.ptr(ia), _lib.ptr(ib),
+                                           batch_size, channels, height, width, nr, pooled_height, pooled_width,
+                                           spatial_scale, sampling_ratio, int(aligned), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr(ga.device)), "roi_align_bwd2")
+    return ia, ib
+
+
+@roi_align_pair_backward.register_fake
+def _(grad_a, grad_b, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width,
+      sampling_ratio, aligned):
+    shape = (batch_size, channels, height, width)
+    return grad_a.new_empty(shape), grad_a.new_empty(shape)
+
+
+def _roi_pair_setup(ctx, inputs, output):
+    input_a, _, rois, scale, ph, pw, sr, aligned = inputs
+    ctx.save_for_backward(rois)
+    ctx.meta = (scale, ph, pw, tuple(input_a.shape), sr, aligned)
+
+
+def _roi_pair_bwd(ctx, grad_a, grad_b):
+    (rois,) = ctx.saved_tensors
+    scale, ph, pw, (n, c, h, w), sr, aligned = ctx.meta
+    ga = gb = None
+    if ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+        ga, gb = roi_align_pair_backward(grad_a, grad_b, rois, scale, ph, pw, n, c, h, w, sr, aligned)
+    elif ctx.needs_input_grad[0]:
+        ga = roi_align_backward(grad_a, rois, scale, ph, pw, n, c, h, w, sr, aligned)
+    elif ctx.needs_input_grad[1]:
+        gb = roi_align_backward(grad_b, rois, scale, ph, pw, n, c, h, w, sr, aligned)
+    return ga, gb, None, None, None, None, None, None
+
+
+roi_align_pair.register_autograd(_roi_pair_bwd, setup_context=_roi_pair_setup)
+
+
 # ------------------------------------------------------------------------------------------------ NMS
 @torch.library.custom_op("cddmsl_b200::batched_nms", mutates_args=(), device_types="cuda")
 def batched_nms(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float,

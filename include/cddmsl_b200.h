@@ -58,6 +58,17 @@ int cddmsl_roi_align_bwd(const float* gout, const float* rois, float* gin, int N
                          int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, void* workspace,
                          size_t workspace_bytes, cddmsl_stream_t stream);
 
+/* The same RoIs on TWO feature maps of the same shape: the source / target pair of the region-level consistency
+ * branch, detectron2/modeling/roi_heads/clip_roi_heads.py:117-132 (`forward_get_features` pools features_src and
+ * features_trgt with identical proposal boxes; the reference runs ROIAlign twice).  One plan (per-RoI bands, image
+ * buckets) serves both maps; results are bit-identical to two single calls.  Workspace: the single-map sizes. */
+int cddmsl_roi_align_fwd2(const float* in_a, const float* in_b, const float* rois, float* out_a, float* out_b, int N,
+                          int C, int H, int W, int R, int PH, int PW, float spatial_scale, int sampling_ratio,
+                          int aligned, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+int cddmsl_roi_align_bwd2(const float* gout_a, const float* gout_b, const float* rois, float* gin_a, float* gin_b,
+                          int N, int C, int H, int W, int R, int PH, int PW, float spatial_scale, int sampling_ratio,
+                          int aligned, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+
 /* ---------------------------------------------------------------- piece 2: NMS ------------------ */
 /* boxes [M,4] xyxy, scores [M], idxs [M] class/level ids or NULL.  keep [M] receives the kept ORIGINAL
  * indices ordered by score descending (ties: lower index first); *num_keep (device int32) their count.

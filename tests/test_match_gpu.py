@@ -118,3 +118,80 @@ def test_label_and_sample_proposals_batched():
         rh.BATCHED_IMAGES = True
     assert [len(a) for a in loop] == [len(a) for a in out]
     assert [int((a.gt_classes != k).sum()) for a in loop] == [int((a.gt_classes != k).sum()) for a in out]
+
+
+class _UpstreamMatcher:
+    """The attributes detectron2/modeling/matcher.py:36-61 leaves on a Matcher (thresholds WITH the +-inf sentinels)."""
+
+    def __init__(self, thresholds, labels, allow_low_quality_matches=False):
+        self.thresholds = [-float("inf")] + list(thresholds) + [float("inf")]
+        self.labels = labels
+        self.allow_low_quality_matches = allow_low_quality_matches
+
+
+class _UpstreamROIHeads:
+    """Only what detectron2/modeling/roi_heads/roi_heads.py:140-164 sets on the reference class."""
+
+    def __init__(self, k, only_fg=False):
+        self.num_classes = k
+        self.batch_size_per_image = 512
+        self.positive_fraction = 0.25
+        self.proposal_matcher = _UpstreamMatcher([0.5], [0, 1])
+        self.proposal_append_gt = True
+        self.only_sample_fg_proposals = only_fg
+
+
+def _toy_batch(g, k):
+    from cddmsl_b200.structures import Boxes, Instances
+
+    props, tgts = [], []
+    for ng, nm in [(5, 900), (0, 700), (3, 1100)]:
+        t = Instances((600, 1000))
+        t.gt_boxes = Boxes(synth.make_boxes(ng, 600, 1000, g, min_side=48.0, degenerate_frac=0.0).to(DEV) if ng
+                           else torch.zeros(0, 4, device=DEV))
+        t.gt_classes = torch.randint(0, k, (ng,), generator=g).to(DEV)
+        p = Instances((600, 1000))
+        b = synth.make_boxes(nm, 600, 1000, g, degenerate_frac=0.0)
+        if ng:
+            b[:300] = t.gt_boxes.tensor.cpu()[torch.randint(0, ng, (300,), generator=g)] + torch.randn(300, 4, generator=g) * 5
+        p.proposal_boxes = Boxes(b.to(DEV))
+        p.objectness_logits = torch.randn(nm, generator=g).to(DEV)
+        props.append(p)
+        tgts.append(t)
+    return props, tgts
+
+
+def test_patched_into_an_upstream_shaped_class():
+    """INTEGRATION.md assigns `label_and_sample_proposals` to the REFERENCE's ROIHeads: the function may only use
+    what that class has (no helper methods, the upstream Matcher's attributes)."""
+    from cddmsl_b200.modeling import label_and_sample_proposals
+
+    k = 20
+    props, tgts = _toy_batch(synth.generator(43), k)
+    _UpstreamROIHeads.label_and_sample_proposals = label_and_sample_proposals
+    out = _UpstreamROIHeads(k).label_and_sample_proposals(props, tgts)
+    assert len(out) == 3
+    for o, t in zip(out, tgts):
+        n_fg = int((o.gt_classes != k).sum())
+        assert len(o) <= 512 and n_fg <= 128 and o.has("gt_classes")
+        if len(t):
+            assert o.has("gt_boxes") and len(o.gt_boxes) == len(o)
+
+
+def test_only_sample_fg_proposals():
+    """MODEL.CLIP.ONLY_SAMPLE_FG_PROPOSALS (roi_heads.py:216-228): positives only; an image without ground truth keeps
+    one background proposal."""
+    import cddmsl_b200.modeling.roi_heads as rh
+
+    k = 20
+    props, tgts = _toy_batch(synth.generator(44), k)
+    heads = rh.ROIHeads(num_classes=k, only_sample_fg_proposals=True)
+    for batched in (True, False):
+        rh.BATCHED_IMAGES = batched
+        try:
+            out = heads.label_and_sample_proposals(props, tgts)
+        finally:
+            rh.BATCHED_IMAGES = True
+        assert (out[0].gt_classes != k).all() and 0 < len(out[0]) <= 128
+        assert len(out[1]) == 1 and int(out[1].gt_classes[0]) == k
+        assert (out[2].gt_classes != k).all() and 0 < len(out[2]) <= 128

@@ -98,22 +98,122 @@ def test_seeded_random_vs_oracle(p, sr, aligned, c, hw):
     _close(gin, c_ref.roi_align_bwd(gout, rois, feat.shape, 1.0 / 16, sr, aligned), BWD_RTOL)
 
 
-def test_generic_nchw_kernels_on_the_14x14_shape():
-    """The 14x14 pooler normally takes the channels-last fast path; force the generic NCHW kernels (what runs
-    when no workspace is passed through the C ABI) and hold them to the same oracle."""
+@pytest.mark.parametrize("knobs", [
+    {"roi_pr": 0},                      # round-1 channels-last kernels (forward fallback / default backward)
+    {"roi_pr": 0, "roi_use_cl": 0},     # generic NCHW kernels (what runs when no workspace is passed)
+    {"roi_pr": 3},                      # plane-resident forward AND the transposed backward (experimental knob)
+    {"roi_pr": 1, "roi_pr_chunk": 32},  # many small units per image
+], ids=["channels_last", "generic_nchw", "pr_fwd_bwd", "pr_small_chunks"])
+def test_every_kernel_family_on_the_14x14_shape(knobs):
+    """The 14x14 pooler normally takes the plane-resident forward and the channels-last backward; force every other
+    kernel family through the tuning knobs and hold it to the same oracle."""
     from cddmsl_b200 import _lib
 
     g = synth.generator(55)
     feat = torch.randn(2, 48, 38, 63, generator=g).numpy()
     rois = synth.make_rois(synth.PathConfig("t", 2, 600, 1000, 40, 5), g).numpy()
     gout = torch.randn(rois.shape[0], 48, 14, 14, generator=g).numpy()
-    assert _lib.tune("roi_use_cl", 0)
+    defaults = {"roi_pr": 1, "roi_use_cl": 1, "roi_pr_chunk": 0}
+    for k, v in knobs.items():
+        assert _lib.tune(k, v)
     try:
         o, gin = _run(feat, rois, (14, 14), 1.0 / 16, 0, True, gout=gout)
     finally:
-        _lib.tune("roi_use_cl", 1)
+        for k in knobs:
+            _lib.tune(k, defaults[k])
     _close(o, c_ref.roi_align_fwd(feat, rois, (14, 14), 1.0 / 16, 0, True), FWD_RTOL)
     _close(gin, c_ref.roi_align_bwd(gout, rois, feat.shape, 1.0 / 16, 0, True), BWD_RTOL)
+
+
+def test_wide_bands_and_sparse_sampling_grids():
+    """Plane-resident classes beyond the common ones: RoIs wider than 6 cells per bin (B halves of the records), a
+    fixed sampling grid on huge bins (per-sample path), boxes hanging over every border, on a map with H*W odd."""
+    g = synth.generator(56)
+    feat = torch.randn(1, 6, 33, 131, generator=g).numpy()
+    rois = np.array([[0, 0, 0, 2090, 520], [0, -300, -200, 2400, 700], [0, 5, 5, 1900, 40], [0, 10, 10, 30, 500],
+                     [0, 100, 100, 101, 101], [0, 2000, 400, 2300, 600], [0, 700, 100, 1500, 420]], dtype=np.float32)
+    gout = torch.randn(rois.shape[0], 6, 14, 14, generator=g).numpy()
+    for sr in (0, 1, 2):
+        o, gin = _run(feat, rois, (14, 14), 1.0 / 16, sr, True, gout=gout)
+        _close(o, c_ref.roi_align_fwd(feat, rois, (14, 14), 1.0 / 16, sr, True), FWD_RTOL)
+        _close(gin, c_ref.roi_align_bwd(gout, rois, feat.shape, 1.0 / 16, sr, True), BWD_RTOL)
+
+
+def test_dual_map_equals_two_single_calls():
+    """cddmsl_roi_align_fwd2 / bwd2 (clip_roi_heads.py:117-132: source and target maps, identical boxes): bit-equal
+    to two single calls, gradients flow to both maps."""
+    from cddmsl_b200 import ops
+    from cddmsl_b200.layers import ROIAlign
+
+    g = synth.generator(57)
+    fa = torch.randn(3, 40, 38, 63, generator=g).to(DEV).requires_grad_(True)
+    fb = torch.randn(3, 40, 38, 63, generator=g).to(DEV).requires_grad_(True)
+    rois = synth.make_rois(synth.PathConfig("t", 3, 600, 1000, 16, 5), g).to(DEV)
+    op = ROIAlign((14, 14), 1.0 / 16, 0, aligned=True)
+    oa, ob = op.forward_pair(fa, fb, rois)
+    assert torch.equal(oa, op(fa, rois)) and torch.equal(ob, op(fb, rois))
+    ga, gb = torch.randn_like(oa), torch.randn_like(ob)
+    torch.autograd.backward([oa, ob], [ga, gb])
+    ra = ops.roi_align_backward(ga, rois, 1.0 / 16, 14, 14, 3, 40, 38, 63, 0, True)
+    rb = ops.roi_align_backward(gb, rois, 1.0 / 16, 14, 14, 3, 40, 38, 63, 0, True)
+    _close(fa.grad.cpu().numpy(), ra.cpu().numpy(), BWD_RTOL)   # (atomic order differs between two launches)
+    _close(fb.grad.cpu().numpy(), rb.cpu().numpy(), BWD_RTOL)
+    # a 7x7 pooler on few channels goes through the same entry point
+    op7 = ROIAlign((7, 7), 1.0 / 16, 2, aligned=True)
+    pa, pb = op7.forward_pair(fa.detach()[:, :3].contiguous(), fb.detach()[:, :3].contiguous(), rois)
+    assert torch.equal(pa, op7(fa.detach()[:, :3].contiguous(), rois))
+    assert torch.equal(pb, op7(fb.detach()[:, :3].contiguous(), rois))
+
+
+def test_clip_res5_roi_heads_forward_get_features():
+    """CLIPRes5ROIHeads.forward_get_features (clip_roi_heads.py:117-132): pooler -> res5 -> attnpool on the source
+    and the target map with the same proposal boxes, against the oracle's ROIAlign + the same torch modules."""
+    from cddmsl_b200.modeling import Box2BoxTransform, CLIPRes5ROIHeads, FastRCNNOutputLayers, ROIPooler
+    from cddmsl_b200.structures import Boxes, Instances
+
+    g = synth.generator(58)
+    c, k = 24, 5
+    torch.manual_seed(3)
+    res5 = torch.nn.Sequential(torch.nn.Conv2d(c, 16, 3, stride=2, padding=1), torch.nn.ReLU()).to(DEV)
+    attnpool = lambda x: x.mean(dim=(2, 3))
+    feats_s = torch.randn(2, c, 38, 63, generator=g)
+    feats_t = torch.randn(2, c, 38, 63, generator=g)
+    boxes = [synth.make_boxes(16, 600, 1000, g, degenerate_frac=0.0) for _ in range(2)]
+    props = []
+    for b in boxes:
+        inst = Instances((600, 1000))
+        inst.proposal_boxes = Boxes(b.to(DEV))
+        props.append(inst)
+    w = torch.randn(k, 16, generator=g)
+    head = CLIPRes5ROIHeads(
+        in_features=["res4"], pooler=ROIPooler(14, (1.0 / 16,), 0, "ROIAlignV2"), num_classes=k,
+        box_predictor=FastRCNNOutputLayers(16, box2box_transform=Box2BoxTransform((10.0, 10.0, 5.0, 5.0)),
+                                           num_classes=k, clip_cls_emb=(True, w, "CLIPRes5ROIHeads", 16),
+                                           bg_cls_loss_weight=0.2, openset_test=(None, None, 0.01, 0.5)).to(DEV))
+    head.eval()
+    a_s, a_t = head.forward_get_features({"res4": feats_s.to(DEV)}, {"res4": feats_t.to(DEV)}, props, res5=res5,
+                                         attnpool=attnpool)
+    rois = torch.cat([torch.cat([torch.full((16, 1), float(i)), b], 1) for i, b in enumerate(boxes)]).numpy()
+    for got, f in ((a_s, feats_s), (a_t, feats_t)):
+        pooled = torch.from_numpy(c_ref.roi_align_fwd(f.numpy(), rois, (14, 14), 1.0 / 16, 0, True)).to(DEV)
+        with torch.no_grad():
+            want = attnpool(res5(pooled))
+        _close(got.detach().cpu().numpy(), want.cpu().numpy(), 1e-4)
+    # the training / inference `forward` of the same head (box branch) runs end to end
+    tg = []
+    for b in boxes:
+        t = Instances((600, 1000))
+        t.gt_boxes = Boxes(b[:3].to(DEV))
+        t.gt_classes = torch.tensor([0, 1, 2], device=DEV)
+        tg.append(t)
+    for p in props:
+        p.objectness_logits = torch.zeros(len(p), device=DEV)
+    head.train()
+    _, losses = head.forward(None, {"res4": feats_s.to(DEV)}, props, tg, res5=res5, attnpool=attnpool)
+    assert set(losses) == {"loss_cls", "loss_box_reg"} and all(torch.isfinite(v).all() for v in losses.values())
+    head.eval()
+    inst, _ = head.forward(None, {"res4": feats_s.to(DEV)}, props, None, res5=res5, attnpool=attnpool)
+    assert len(inst) == 2 and all(i.has("pred_boxes") and i.has("scores") for i in inst)
 
 
 def test_rois_in_arbitrary_image_order():
