@@ -43,6 +43,8 @@ def parse():
     p.add_argument("--workload", default="voc", choices=["voc", "city", "tiny"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-extras", action="store_true",
+                   help="skip the extra sections (NMS, LVIS head, Cityscapes shape, library baseline, sweep)")
     p.add_argument("--e2e-d2h", choices=["losses", "grads"], default="losses",
                    help="what the e2e arm reads back every step: the step's result (the three losses, 16 bytes -- in "
                         "training the gradients stay on the device and feed the backbone's backward), or additionally "
@@ -213,7 +215,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, args.gpus),
+            "config": {"workload": f"reference CPU arm (host cores only, rank 0): {sample}",
+                       "full_workload": workload_config(cfg, args.gpus)["workload"],
+                       "rois_per_step": n_img * rpi, "parallelism": f"{cores} host threads",
+                       "note": "a bounded sample of the ours-arm workload per step, not the whole 16 x 512 batch"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -227,6 +232,270 @@ def workload_config(cfg, n_gpus):
                         f"n={cfg.n_images * cfg.regions_per_image}/GPU (256-d), fwd+bwd",
             "rois_per_gpu": cfg.n_rois, "global_rois": cfg.n_rois * n_gpus, "parallelism": f"dp{n_gpus} (by image)",
             "l2_policy": "inputs larger than L2 (6.6 GB pooled tensor, 157 MB feature map per step)"}
+
+
+# ------------------------------------------------------------------------------------- device step
+def make_state(cfg, rank, world, dev, ops, dist, seed_offset=0):
+    """Synthetic inputs of one workload resident in HBM + the device-timed step over the C-ABI-backed ops.
+    The two alignment losses (pack -> all-gather -> loss, gradient in the same pass) run on a SIDE stream concurrent
+    with the ROIAlign forward: nothing in the ROIAlign / head chain depends on them (rcnn.py runs them as separate
+    forward passes of the model)."""
+    g = synth.generator(cfg.seed + 1000 * rank + seed_offset)
+    P, scale = cfg.pooled, 1.0 / cfg.stride
+    h_feat = synth.make_features(cfg, g).pin_memory()
+    h_rois = synth.make_rois(cfg, g).pin_memory()
+    hx, hw, hwbg, hgt = synth.make_head_inputs(cfg, g)
+    hx, hgt = hx.pin_memory(), hgt.pin_memory()
+    h_align = [t.pin_memory() for t in synth.make_align_inputs(cfg, g)]
+    R, N, C = cfg.n_rois, cfg.n_images, cfg.channels
+    Hf, Wf = cfg.feat_hw
+    feat, rois, x, gt = h_feat.to(dev), h_rois.to(dev), hx.to(dev), hgt.to(dev)
+    w, w_bg = hw.to(dev), hwbg.to(dev)
+    a_is, a_it, a_rs, a_rt = [t.to(dev) for t in h_align]
+    one = torch.ones(1, device=dev)
+    side = torch.cuda.Stream(dev)
+    last = {}
+
+    def align_fused(a, b, tag):
+        packed, norms = ops.align_pack(a, b)
+        if world > 1:
+            allp = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
+            dist.all_gather_into_tensor(allp, packed)
+        else:
+            allp = packed.unsqueeze(0)
+        last[tag] = allp
+        return ops.align_loss(allp, norms, rank, one, True)
+
+    def events(steps):
+        return [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
+
+    def device_step(e=None):
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if e: e[4].record(side)
+            l_img = align_fused(a_it, a_is, "image")
+            l_reg = align_fused(a_rs, a_rt, "region")
+            if e: e[5].record(side)
+        if e: e[0].record()
+        out = ops.roi_align(feat, rois, scale, P, P, cfg.sampling_ratio, True)
+        if e: e[1].record()
+        loss, _, dx, stats = ops.clip_head_loss(x, w, w_bg, gt, cfg.temperature, ops.LOSS_FOCAL, cfg.focal_gamma,
+                                                cfg.bg_weight, one, False, False, True)
+        if e: e[2].record()
+        gin = ops.roi_align_backward(out, rois, scale, P, P, N, C, Hf, Wf, cfg.sampling_ratio, True)
+        if e: e[3].record()
+        main.wait_stream(side)
+        for t in (l_img + l_reg):
+            t.record_stream(main)
+        return loss, l_img[0], l_reg[0], gin, dx
+
+    return {"host": (h_feat, h_rois, hx, hw, hgt, h_align), "R": R, "N": N, "C": C, "feat_hw": (Hf, Wf), "P": P,
+            "scale": scale, "one": one, "step": device_step, "events": events, "gathered": last,
+            "dev_inputs": (feat, rois, x, w, w_bg, gt)}
+
+
+def timed_median(fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def closed_form_alignment(allp):
+    """(CE(S, I) + CE(S^T, I)) / 2 with S = A B^T from the gathered, already normalised rows: what every rank's fused
+    kernel must report (rcnn.py:458-468), evaluated with plain torch ops."""
+    import torch.nn.functional as F
+
+    a = allp[:, 0].reshape(-1, allp.shape[-1])
+    b = allp[:, 1].reshape(-1, allp.shape[-1])
+    sm = a @ b.t()
+    gt = torch.arange(sm.shape[0], device=sm.device)
+    return float((F.cross_entropy(sm, gt) + F.cross_entropy(sm.t(), gt)) / 2)
+
+
+def extra_sections(args, rank, world, dev, ops, dist, peak):
+    """Driver-visible numbers for the other BASELINE.json configs (extra keys of the JSON line; the headline stays
+    configs[1]): NMS (part of the north_star path, its own unit), the LVIS-scale tcgen05 head (configs[3]), the
+    Cityscapes shape at the current N incl. the all-gather (configs[2]), what the reference runs on a GPU today
+    (torchvision CUDA + eager PyTorch) on the headline inputs, and a bounded subset of the sweep (configs[4])."""
+    from cddmsl_b200 import _lib
+    from cddmsl_b200.layers import batched_nms, batched_nms_images
+
+    ex = {}
+    # ---- configs[2]: Cityscapes shape, every rank, all-gather included
+    if args.workload != "city":
+        cfg = synth.CONFIGS["city"]
+        st = make_state(cfg, rank, world, dev, ops, dist)
+        k = 5
+        evs = st["events"](k)
+        for _ in range(3):
+            r_ = st["step"]()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(k):
+            r_ = st["step"](evs[i])
+        t1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        fwd = statistics.mean(evs[i][0].elapsed_time(evs[i][1]) for i in range(k))
+        bwd = statistics.mean(evs[i][2].elapsed_time(evs[i][3]) for i in range(k))
+        al = statistics.mean(evs[i][4].elapsed_time(evs[i][5]) for i in range(k))
+        Hf, Wf = st["feat_hw"]
+        b_roi = st["R"] * (4 * st["C"] * 196 + 20) + st["N"] * st["C"] * Hf * Wf * 4
+        dom = max(fwd, bwd)
+        ex["city"] = {"workload": f"configs[2]: per GPU {cfg.n_images} images 1024x2048 -> res4 1024x{Hf}x{Wf}, "
+                                  f"{cfg.rois_per_image} RoIs/img, K=8, alignment n={cfg.n_images * 16 * world} gathered "
+                                  f"rows over {world} rank(s)",
+                      "value": world * st["R"] * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k, "steps": k,
+                      "roi_align_fwd_ms": round(fwd, 4), "roi_align_bwd_ms": round(bwd, 4),
+                      "align_x2_incl_allgather_ms": round(al, 4),
+                      "roofline": {"bound": "hbm", "kernel": "roi_align_bwd" if bwd >= fwd else "roi_align_fwd",
+                                   "achieved": b_roi / (dom * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": b_roi / (dom * 1e-3) / 1e9 / peak, "frac_fwd": b_roi / (fwd * 1e-3) / 1e9 / peak,
+                                   "frac_bwd": b_roi / (bwd * 1e-3) / 1e9 / peak, "bytes": b_roi},
+                      "losses": [float(v) for v in r_[:3]]}
+        del st, r_, evs
+        torch.cuda.empty_cache()
+    if world > 1 or rank != 0:
+        return ex
+    # ---- NMS: an RPN batch, 16 images x 12 000 proposals @ 0.7 in ONE call (proposal_utils.py:95-116 loops per image)
+    g = synth.generator(77)
+    nb, m = 16, 12000
+    bx, sc = [], []
+    for _ in range(nb):
+        b_, s_, _ = synth.make_nms_inputs(m, 600, 1000, g, num_classes=1)
+        bx.append(b_)
+        sc.append(s_)
+    boxes, scores = torch.stack(bx).to(dev), torch.stack(sc).to(dev)
+    counts = torch.full((nb,), m, dtype=torch.int32, device=dev)
+    keep, nk = batched_nms_images(boxes, scores, None, counts, 0.7)
+    t_b = timed_median(lambda: batched_nms_images(boxes, scores, None, counts, 0.7), 10)
+    t_1 = timed_median(lambda: batched_nms(boxes[0], scores[0], torch.zeros(m, dtype=torch.int64, device=dev), 0.7), 10)
+    nms_bytes = nb * (28 * m + 8 * m * ((m + 63) // 64))
+    ex["nms"] = {"workload": f"RPN batch {nb} x {m} boxes, IoU 0.7, one class (C4: one level)", "ms": round(t_b, 4),
+                 "boxes_per_s": nb * m / (t_b * 1e-3), "kept_per_image_mean": float(nk.float().mean()),
+                 "single_image_12000_ms": round(t_1, 4), "algorithmic_bytes": nms_bytes,
+                 "gbs": nms_bytes / (t_b * 1e-3) / 1e9, "frac_of_hbm_peak": nms_bytes / (t_b * 1e-3) / 1e9 / peak,
+                 "bound": "the greedy scan (serial over 64-box blocks), not bandwidth (SURVEY 8d)"}
+    ex["_nms_spot"] = (boxes[0, :3000].cpu(), scores[0, :3000].cpu())
+    del boxes, scores, keep
+    # ---- configs[3]: LVIS-scale head on tcgen05 (3xTF32), fwd + bwd
+    r, d, k = 65536, 1024, 1203
+    g = synth.generator(3)
+    x = torch.randn(r, d, generator=g).to(dev)
+    w = torch.randn(k, d, generator=g).to(dev)
+    w_bg = torch.zeros(1, d, device=dev)
+    gt = torch.randint(0, k + 1, (r,), generator=g).to(dev)
+    one = torch.ones(1, device=dev)
+    head = lambda: ops.clip_head_loss(x, w, w_bg, gt, 0.01, ops.LOSS_FOCAL, 0.5, 0.2, one, False, True, True)
+    t_h = timed_median(head, 5)
+    flops = 2 * 2.0 * r * d * (k + 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    ex["lvis_head"] = {"workload": f"configs[3]: {r} RoIs x {k} concepts + bg, D={d}, cosine logits + focal CE + dx "
+                                   "(logits materialised)", "ms": round(t_h, 4), "rois_per_s": r / (t_h * 1e-3),
+                       "algorithmic_TFLOPs": flops / (t_h * 1e-3) / 1e12,
+                       "tensor_TFLOPs_issued_3xTF32": 3 * flops / (t_h * 1e-3) / 1e12,
+                       "frac_of_tf32_peak_issued": 3 * flops / (t_h * 1e-3) / 1e12 / (bf16 / 2),
+                       "tf32_peak_assumed_TFLOPs": bf16 / 2,
+                       "peak_note": "TF32 dense peak taken as half the measured bf16 cuBLAS throughput of MEASURED_PEAKS.json",
+                       "tensor_pipe_evidence": "profiles/ (ncu capture + SASS listing of gemm_tf32x3_kernel)"}
+    del x, w, gt
+    torch.cuda.empty_cache()
+    # ---- what the reference runs on a GPU today: torchvision CUDA ROIAlign + eager head, same inputs as the headline
+    try:
+        import torch.nn.functional as F
+        from torchvision.ops import roi_align as tv_roi_align
+        from torchvision.ops.boxes import batched_nms as tv_batched_nms
+
+        cfg = synth.CONFIGS[args.workload]
+        st = make_state(cfg, rank, world, dev, ops, dist)
+        feat, rois, x, w, w_bg, gt = st["dev_inputs"]
+        P, scale = st["P"], st["scale"]
+        tv_f = timed_median(lambda: tv_roi_align(feat, rois, (P, P), scale, cfg.sampling_ratio, True), 3, warm=1)
+        fr = feat.detach().requires_grad_(True)
+        o = tv_roi_align(fr, rois, (P, P), scale, cfg.sampling_ratio, True)
+        go = torch.ones_like(o)
+        tv_b = timed_median(lambda: torch.autograd.grad(o, fr, go, retain_graph=True), 3, warm=1)
+        del o, go, fr
+        kk = cfg.num_classes
+
+        def eager_head():
+            xx = x.detach().requires_grad_(True)
+            nx = F.normalize(xx, p=2.0, dim=1)
+            s_ = torch.cat((nx @ F.normalize(w, p=2.0, dim=1).t(), F.linear(nx, w_bg)), dim=1) / cfg.temperature
+            ce = F.cross_entropy(s_, gt, reduction="none")
+            pt = F.softmax(s_, dim=-1)[torch.arange(s_.size(0), device=dev), gt]
+            loss = ce * ((1 - pt) ** cfg.focal_gamma)
+            lw = torch.ones(loss.size(0), device=dev)
+            lw[gt == kk] = cfg.bg_weight
+            (loss * lw).mean().backward()
+
+        t_eh = timed_median(eager_head, 5)
+        b0, s0, _ = synth.make_nms_inputs(12000, 600, 1000, synth.generator(77), num_classes=1)
+        b0, s0 = b0.to(dev), s0.to(dev)
+        z = torch.zeros(12000, dtype=torch.int64, device=dev)
+        t_tn = timed_median(lambda: tv_batched_nms(b0, s0, z, 0.7), 5)
+        ex["library_baseline"] = {"what": "the kernels the reference reaches on a GPU today, same inputs, same B200: "
+                                          "torchvision CUDA roi_align / _roi_align_backward / nms, eager PyTorch head",
+                                  "torchvision_roi_align_fwd_ms": round(tv_f, 3), "torchvision_roi_align_bwd_ms": round(tv_b, 3),
+                                  "eager_head_fwd_bwd_ms": round(t_eh, 4), "torchvision_nms_12000_ms": round(t_tn, 4)}
+        del st, feat, rois
+        torch.cuda.empty_cache()
+    except Exception as e:  # torchvision absent: say so instead of failing the bench
+        ex["library_baseline"] = {"unavailable": repr(e)[:200]}
+    # ---- configs[4]: a bounded subset of the ROIAlign / NMS sweep
+    sweep = {"roi_align": [], "nms": []}
+    vc = synth.CONFIGS["voc"]
+    for r_total, c in ((1024, 1024), (16384, 1024), (65536, 256)):
+        cfg = synth.PathConfig("sweep", 16, 600, 1000, r_total // 16, 20, channels=c, seed=4)
+        g = synth.generator(4)
+        feat = synth.make_features(cfg, g).to(dev)
+        rois = synth.make_rois(cfg, g).to(dev)
+        for p in (7, 14):
+            for sr in (0, 2):
+                out = ops.roi_align(feat, rois, 1.0 / 16, p, p, sr, True)
+                tf = timed_median(lambda: ops.roi_align(feat, rois, 1.0 / 16, p, p, sr, True), 3, warm=1)
+                tb = timed_median(lambda: ops.roi_align_backward(out, rois, 1.0 / 16, p, p, 16, c, 38, 63, sr, True), 3, warm=1)
+                by = r_total * (4 * c * p * p + 20) + 16 * c * 38 * 63 * 4
+                sweep["roi_align"].append({"rois": r_total, "channels": c, "bins": p, "sampling_ratio": sr,
+                                           "fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4),
+                                           "fwd_frac": by / (tf * 1e-3) / 1e9 / peak, "bwd_frac": by / (tb * 1e-3) / 1e9 / peak})
+                del out
+        del feat, rois
+        torch.cuda.empty_cache()
+    for m_ in (1000, 4000, 16000, 64000):
+        for ncls in (1, 20):
+            b0, s0, i0 = synth.make_nms_inputs(m_, 600, 1000, synth.generator(4), num_classes=ncls)
+            b0, s0, i0 = b0.to(dev), s0.to(dev), i0.to(dev)
+            tn = timed_median(lambda: batched_nms(b0, s0, i0, 0.7), 3, warm=1)
+            sweep["nms"].append({"boxes": m_, "classes": ncls, "ms": round(tn, 4), "boxes_per_s": m_ / (tn * 1e-3)})
+    sweep["note"] = ("subset of configs[4] (1k-256k RoIs: the 256k point needs 51 GB per tensor at C=256 and is left to "
+                     "tools/roi_sweep.py); host-CPU column: cpu_baseline (ROIAlign+head, configs[0]) and nms.cpu_check")
+    ex["sweep"] = sweep
+    return ex
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -255,46 +524,11 @@ def run_ours(args):
         assert _lib.tune(k, int(v)), f"unknown tuning key {k}"
 
     cfg = synth.CONFIGS[args.workload]
-    g = synth.generator(cfg.seed + 1000 * rank)
-    P, scale = cfg.pooled, 1.0 / cfg.stride
-    h_feat = synth.make_features(cfg, g).pin_memory()
-    h_rois = synth.make_rois(cfg, g).pin_memory()
-    hx, hw, hwbg, hgt = synth.make_head_inputs(cfg, g)
-    hx, hgt = hx.pin_memory(), hgt.pin_memory()
-    h_align = [t.pin_memory() for t in synth.make_align_inputs(cfg, g)]
-    R, N, C = cfg.n_rois, cfg.n_images, cfg.channels
-    Hf, Wf = cfg.feat_hw
-
-    feat, rois, x, gt = h_feat.to(dev), h_rois.to(dev), hx.to(dev), hgt.to(dev)
-    w, w_bg = hw.to(dev), hwbg.to(dev)
-    a_is, a_it, a_rs, a_rt = [t.to(dev) for t in h_align]
-    one = torch.ones(1, device=dev)
-
-    def align_fused(a, b):
-        packed, norms = ops.align_pack(a, b)
-        if world > 1:
-            allp = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
-            dist.all_gather_into_tensor(allp, packed)
-        else:
-            allp = packed.unsqueeze(0)
-        return ops.align_loss(allp, norms, rank, one, True)
-
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
-
-    def device_step(i=None):
-        e = ev[i] if i is not None else None
-        if e: e[0].record()
-        out = ops.roi_align(feat, rois, scale, P, P, cfg.sampling_ratio, True)
-        if e: e[1].record()
-        loss, _, dx, stats = ops.clip_head_loss(x, w, w_bg, gt, cfg.temperature, ops.LOSS_FOCAL, cfg.focal_gamma,
-                                                cfg.bg_weight, one, False, False, True)
-        if e: e[2].record()
-        l_img = align_fused(a_it, a_is)
-        l_reg = align_fused(a_rs, a_rt)
-        if e: e[3].record()
-        gin = ops.roi_align_backward(out, rois, scale, P, P, N, C, Hf, Wf, cfg.sampling_ratio, True)
-        if e: e[4].record()
-        return loss, l_img[0], l_reg[0], gin, dx
+    st = make_state(cfg, rank, world, dev, ops, dist)
+    h_feat, h_rois, hx, hw, hgt, h_align = st["host"]
+    R, N, C, (Hf, Wf), P, scale = st["R"], st["N"], st["C"], st["feat_hw"], st["P"], st["scale"]
+    one = st["one"]
+    device_step, ev = st["step"], st["events"](args.steps)
 
     def barrier():
         if world > 1:
@@ -318,7 +552,7 @@ def run_ours(args):
     barrier()
     t0.record()
     for i in range(args.steps):
-        res = device_step(i)
+        res = device_step(ev[i])
     t1.record()
     barrier()
     launches = _lib.launch_count() - launches0
@@ -327,11 +561,27 @@ def run_ours(args):
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    seg_all = [[ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)] for j in range(4)]
+    # main stream: [0] roi fwd [1] head [2] roi bwd [3]; side stream: [4] align x2 [5]
+    pairs = [(0, 1), (1, 2), (4, 5), (2, 3)]
+    seg_all = [[ev[i][a].elapsed_time(ev[i][b]) for i in range(args.steps)] for a, b in pairs]
     seg = [statistics.mean(v) for v in seg_all]
     seg_minmax = [(min(v), statistics.median(v), max(v)) for v in seg_all]
     mstats = torch.cuda.memory_stats(dev)
     losses = [float(v) for v in res[:3]]
+    # every rank's fused alignment kernels against the closed form on the gathered (NCCL) buffer
+    align_check = {}
+    for tag, got in (("image", losses[1]), ("region", losses[2])):
+        want = closed_form_alignment(st["gathered"][tag])
+        align_check[tag] = {"fused": got, "torch_closed_form": want, "rel_err": abs(got - want) / max(abs(want), 1e-12),
+                            "gathered_rows": int(st["gathered"][tag].shape[0] * st["gathered"][tag].shape[2])}
+    align_ok = all(v["rel_err"] <= 1e-5 for v in align_check.values())
+    if world > 1:
+        tt = torch.tensor([1.0 if align_ok else 0.0], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        align_ok = bool(tt.item() > 0.5)
+    align_check["ok_on_every_rank"] = align_ok
+    if not align_ok:
+        raise SystemExit(f"bench.py: alignment loss disagrees with the closed form on the gathered buffer: {align_check}")
 
     # ---------------- end to end through the reference-shaped API, host buffers in and out every step
     e2e = None
@@ -443,6 +693,36 @@ def run_ours(args):
                       else "losses + every gradient of the path",
                "pipelining": "H2D(i+1) and D2H(i-1) on side streams overlap compute(i); all copies inside the timed region",
                "numa_bound_cpus": numa_cpus}
+        # the box's host->device ceiling with all ranks copying at once (what bounds e2e beyond one GPU: every rank
+        # uploads its 157 MB feature map per step, which in training never leaves the GPU)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 6
+        p0.record()
+        for _ in range(reps):
+            dev_in[0][0].copy_(h_feat, non_blocking=True)
+        p1.record()
+        barrier()
+        gbs = reps * h_feat.numel() * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        agg = gbs
+        if world > 1:
+            tt = torch.tensor([gbs], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            agg = float(tt.item())
+        e2e["h2d_probe"] = {"what": f"{world} rank(s) copying their pinned 157 MB map to HBM concurrently, nothing else running",
+                            "gbs_rank0": gbs, "gbs_all_ranks": agg,
+                            "e2e_h2d_gbs_per_rank_achieved": h2d / (ms2 / k2 * 1e-3) / 1e9,
+                            "e2e_upper_bound_from_h2d": world * R / (h2d / (agg / world * 1e9)) if agg > 0 else None}
+    extras = {}
+    if not args.no_extras:
+        peaks0 = {}
+        try:
+            peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        del res
+        torch.cuda.empty_cache()
+        extras = extra_sections(args, rank, world, dev, ops, dist, float(peaks0.get("hbm_gbs", 6650.0)))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -460,6 +740,7 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bytes_roi = R * (4 * C * P * P + 20) + N * C * Hf * Wf * 4
     names = ["roi_align_fwd", "clip_head_fwd_bwd", "align_loss_x2_fwd_bwd", "roi_align_bwd"]
+    # (the alignment segment runs on a side stream concurrently with roi_align_fwd; its time is its own duration)
     kern = {n: {"ms": round(seg[j], 4), "ms_min_med_max": [round(x, 4) for x in seg_minmax[j]]}
             for j, n in enumerate(names)}
     kern["allocator"] = {"num_device_alloc": int(mstats.get("num_device_alloc", 0)),
@@ -473,14 +754,19 @@ def run_ours(args):
     ach = kern[dom]["gbs"]
     step_bytes = 2 * bytes_roi + head_bytes
     traffic = None
+    traffic_src = None
     try:  # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["kernels"]
-        key = "roi_align_bwd_cl" if dom == "roi_align_bwd" else "roi_align_fwd_cl"
-        traffic = next(v["dram_bytes"] for k, v in tj.items() if k.startswith(key)) if args.workload == "voc" else None
+        tfile = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
+        key = "roi_align_bwd" if dom == "roi_align_bwd" else "roi_align_fwd"
+        if args.workload == "voc":
+            traffic = next(v["dram_bytes"] for k, v in tfile["kernels"].items() if k.startswith(key))
+            traffic_src = tfile.get("capture")
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_capture": traffic_src, "peak_source": peak_src,
+                "kernels_frac": {"roi_align_fwd": kern["roi_align_fwd"]["gbs"] / peak,
+                                 "roi_align_bwd": kern["roi_align_bwd"]["gbs"] / peak},
                 "step_frac": (step_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
                 "step_algorithmic_bytes": step_bytes}
 
@@ -491,6 +777,19 @@ def run_ours(args):
         ref = synth.CONFIGS["cpu_ref"]
         cpu_reference_step(ref, 1, 32, 1)  # warm-up
         dt, r = cpu_reference_step(ref, ref.n_images, ref.rois_per_image, ref.seed)
+        spot = extras.pop("_nms_spot", None)
+        if spot is not None:   # bit-exact spot check of the NMS path against the oracle's C restatement (checker only)
+            from oracle import c_ref
+            from cddmsl_b200.layers import batched_nms as _bn
+
+            b0, s0 = spot
+            t_c0 = time.perf_counter()
+            want = c_ref.batched_nms(b0.numpy(), s0.numpy(), None, 0.7)
+            t_c = time.perf_counter() - t_c0
+            got = _bn(b0.to(dev), s0.to(dev), torch.zeros(len(s0), dtype=torch.int64, device=dev), 0.7).cpu().numpy()
+            extras["nms"]["cpu_check"] = {"boxes": int(len(s0)), "kept": int(len(want)),
+                                          "bit_exact": bool(len(got) == len(want) and (got == want).all()),
+                                          "oracle_c_port_ms": round(t_c * 1e3, 3)}
         cpu_baseline = {"value": r / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
                         "sample": "BASELINE.json configs[0]: 2 images x 512 RoIs (38x63 map, 1024 ch, 14x14, K=20) "
                                   "fwd+bwd once, torchvision CPU ops + ATen via oracle/torch_ref.py, all host threads"}
@@ -500,7 +799,10 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kern,
-            "losses": {"loss_cls": losses[0], "align_image": losses[1], "align_region": losses[2]}}
+            "losses": {"loss_cls": losses[0], "align_image": losses[1], "align_region": losses[2]},
+            "align_check": align_check}
+    extras.pop("_nms_spot", None)
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -140,6 +140,55 @@ def test_world_emulation_vs_oracle(world, n_local, dim):
         _close(db.cpu().numpy(), br.grad[sl].numpy(), 1e-4, "db")
 
 
-def test_two_gpus_nccl_if_available():
+def _nccl_worker(rank, world, port, golden_dir, q):
+    import torch.distributed as dist
+
+    from cddmsl_b200.modeling import caption_consistency_loss, image_caption_consistency_loss
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        out = {}
+        for name, fn, kind in (("align_world2.npz", caption_consistency_loss, ""),
+                               ("align_ref.npz", caption_consistency_loss, "w2_region_"),
+                               ("align_ref.npz", image_caption_consistency_loss, "w2_image_")):
+            w = np.load(os.path.join(golden_dir, name))
+            pre = "w2_" if kind else ""
+            a = torch.from_numpy(w[f"{pre}a{rank}"]).to(dev).requires_grad_(True)
+            b = torch.from_numpy(w[f"{pre}b{rank}"]).to(dev).requires_grad_(True)
+            loss = fn(a, b)
+            loss.backward()
+            out[kind or "world2_"] = (loss.item(), a.grad.cpu().numpy(), b.grad.cpu().numpy())
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_over_nccl(golden_dir):
+    """The real thing: two processes, two GPUs, NCCL all-gather inside `caption_consistency_loss`, against the fixtures
+    the reference's own GatherLayer + rcnn.py lines produced under gloo."""
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (covered by bench.py --gpus 2 and the gloo host-logic test)")
+        pytest.skip("needs 2 GPUs (run with `gpurun --gpus 2`; the gloo host-logic test covers the N > 1 path on CPU)")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, 29611, golden_dir, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    w1 = np.load(os.path.join(golden_dir, "align_world2.npz"))
+    w2 = np.load(os.path.join(golden_dir, "align_ref.npz"))
+    for r in range(2):
+        loss, da, db = res[r]["world2_"]
+        _close(loss, w1["loss"], 1e-5, "loss")
+        _close(da, w1[f"da{r}"], 1e-4, f"da{r}")
+        _close(db, w1[f"db{r}"], 1e-4, f"db{r}")
+        for kind in ("w2_region_", "w2_image_"):
+            loss, da, db = res[r][kind]
+            _close(loss, w2[f"{kind}loss"], 1e-5, kind + "loss")
+            _close(da, w2[f"{kind}da{r}"], 1e-4, kind + "da")
+            _close(db, w2[f"{kind}db{r}"], 1e-4, kind + "db")
