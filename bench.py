@@ -237,9 +237,10 @@ def workload_config(cfg, n_gpus):
 # ------------------------------------------------------------------------------------- device step
 def make_state(cfg, rank, world, dev, ops, dist, seed_offset=0):
     """Synthetic inputs of one workload resident in HBM + the device-timed step over the C-ABI-backed ops.
-    The two alignment losses (pack -> all-gather -> loss, gradient in the same pass) run on a SIDE stream concurrent
-    with the ROIAlign forward: nothing in the ROIAlign / head chain depends on them (rcnn.py runs them as separate
-    forward passes of the model)."""
+    The two alignment losses (pack -> all-gather -> loss, gradient in the same pass) are issued first, on the same
+    stream: a side stream was measured and rejected -- the persistent ROIAlign kernels own every SM (one CTA per SM,
+    220 KB of shared memory), so a concurrently issued NCCL all-gather waits for them anyway and, at N = 2, stalled
+    the peer rank for up to 19 ms (6.4 ms/step instead of 4.5)."""
     g = synth.generator(cfg.seed + 1000 * rank + seed_offset)
     P, scale = cfg.pooled, 1.0 / cfg.stride
     h_feat = synth.make_features(cfg, g).pin_memory()
@@ -253,7 +254,6 @@ def make_state(cfg, rank, world, dev, ops, dist, seed_offset=0):
     w, w_bg = hw.to(dev), hwbg.to(dev)
     a_is, a_it, a_rs, a_rt = [t.to(dev) for t in h_align]
     one = torch.ones(1, device=dev)
-    side = torch.cuda.Stream(dev)
     last = {}
 
     def align_fused(a, b, tag):
@@ -270,13 +270,10 @@ def make_state(cfg, rank, world, dev, ops, dist, seed_offset=0):
         return [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
 
     def device_step(e=None):
-        main = torch.cuda.current_stream(dev)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            if e: e[4].record(side)
-            l_img = align_fused(a_it, a_is, "image")
-            l_reg = align_fused(a_rs, a_rt, "region")
-            if e: e[5].record(side)
+        if e: e[4].record()
+        l_img = align_fused(a_it, a_is, "image")
+        l_reg = align_fused(a_rs, a_rt, "region")
+        if e: e[5].record()
         if e: e[0].record()
         out = ops.roi_align(feat, rois, scale, P, P, cfg.sampling_ratio, True)
         if e: e[1].record()
@@ -285,9 +282,6 @@ def make_state(cfg, rank, world, dev, ops, dist, seed_offset=0):
         if e: e[2].record()
         gin = ops.roi_align_backward(out, rois, scale, P, P, N, C, Hf, Wf, cfg.sampling_ratio, True)
         if e: e[3].record()
-        main.wait_stream(side)
-        for t in (l_img + l_reg):
-            t.record_stream(main)
         return loss, l_img[0], l_reg[0], gin, dx
 
     return {"host": (h_feat, h_rois, hx, hw, hgt, h_align), "R": R, "N": N, "C": C, "feat_hw": (Hf, Wf), "P": P,
@@ -561,7 +555,7 @@ def run_ours(args):
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    # main stream: [0] roi fwd [1] head [2] roi bwd [3]; side stream: [4] align x2 [5]
+    # [4] align x2 [5] = [0] roi fwd [1] head [2] roi bwd [3]
     pairs = [(0, 1), (1, 2), (4, 5), (2, 3)]
     seg_all = [[ev[i][a].elapsed_time(ev[i][b]) for i in range(args.steps)] for a, b in pairs]
     seg = [statistics.mean(v) for v in seg_all]
@@ -740,7 +734,7 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bytes_roi = R * (4 * C * P * P + 20) + N * C * Hf * Wf * 4
     names = ["roi_align_fwd", "clip_head_fwd_bwd", "align_loss_x2_fwd_bwd", "roi_align_bwd"]
-    # (the alignment segment runs on a side stream concurrently with roi_align_fwd; its time is its own duration)
+
     kern = {n: {"ms": round(seg[j], 4), "ms_min_med_max": [round(x, 4) for x in seg_minmax[j]]}
             for j, n in enumerate(names)}
     kern["allocator"] = {"num_device_alloc": int(mstats.get("num_device_alloc", 0)),
