@@ -29,7 +29,7 @@ namespace cddmsl {
 
 constexpr int kPrNW = 14;       // longest band (cells) a record holds; longer bands take the per-sample path
 constexpr int kPrMaxG = 32;     // samples per bin and axis the planner merges; beyond: per-sample path
-constexpr int kPrThreads = 512;
+constexpr int kPrThreads = 576;
 constexpr int kPrWarps = kPrThreads / 32;
 constexpr int kPrNB = 4;        // cost buckets per image (heaviest first): units start with the expensive RoIs and
                                 // concurrently running warps mostly execute the same code variant
@@ -711,69 +711,48 @@ __device__ __forceinline__ void pr_red_global(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// Per-warp state of the horizontal (transposed) pass.
+// Per-lane state of one 16-column pass: the lane owns (part of) footprint column `col`.
 template <int CPL>
-struct PrBwdCtx {
-  float* gimg;      // gin + (img * C + cbase + D * slot) * H * W: this slot's first channel plane
-  float* scratch;   // [SLOTS][16][4]
-  const float* tbl; // inverse x table: [virtual column][nps] weights
-  const int* tpa;   // [virtual column] first bin of the lane's (shifted) window of bins
-  int HW, W, H, x0, fw, nps, nv, logl, slot, xi, p;
-  bool act[CPL];    // channel pass exists (ragged last group)
+struct PrBwdCol {
+  const float* gq;   // grad tile + slot's first channel + first bin of this lane's window of bins
+  const float* wt;   // [nps] weights of those bins for this column (shared memory)
+  float* gcol;       // gin + slot's first channel plane + x0 + col
+  int nps, logl, HW, W, H;
+  bool red;          // this lane writes the column (first lane of the column, column inside the footprint)
+  bool act[CPL];     // channel pass exists (ragged last group)
 };
 
-// gin[y][x0 + col] += sum_i tbl[v][i] * u[tpa[v] + i] for every footprint column, all CPL channel passes
 template <int CPL>
-__device__ __forceinline__ void pr_bwd_flush(const PrBwdCtx<CPL>& c, int y, const float (&u)[CPL]) {
+__device__ __forceinline__ void pr_bwd_red(const PrBwdCol<CPL>& c, int y, const float (&u)[CPL]) {
   using M = PrMap<14, CPL>;
-  if (y < 0 || y >= c.H) return;  // rows beyond the map only ever collect zero weights
-  float* sline = c.scratch + c.slot * 64;
-  if (CPL == 4) {
-    *reinterpret_cast<float4*>(sline + c.p * 4) = make_float4(u[0], u[1 % CPL], u[2 % CPL], u[3 % CPL]);
-  } else {
+  if (c.red && y >= 0 && y < c.H) {  // rows beyond the map only ever collect zero weights
+    float* g = c.gcol + (size_t)y * c.W;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) sline[c.p * 4 + k] = u[k];
+    for (int k = 0; k < CPL; ++k)
+      if (c.act[k]) pr_red_global(g + (size_t)M::koff(k) * c.HW, u[k]);
   }
-  __syncwarp();
-  float* grow = c.gimg + (size_t)y * c.W + c.x0;
-  for (int v = c.xi; v < c.nv; v += 16) {
-    const float* wt = c.tbl + v * c.nps;
-    const float* sc = sline + c.tpa[v] * 4;
-    float t[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) t[k] = 0.f;
-    for (int i = 0; i < c.nps; ++i) {
-      const float w = wt[i];
-      if (CPL == 4) {
-        const float4 q = *reinterpret_cast<const float4*>(sc + 4 * i);
-        t[0] = fmaf(w, q.x, t[0]);
-        t[1 % CPL] = fmaf(w, q.y, t[1 % CPL]);
-        t[2 % CPL] = fmaf(w, q.z, t[2 % CPL]);
-        t[3 % CPL] = fmaf(w, q.w, t[3 % CPL]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) t[k] = fmaf(w, sc[4 * i + k], t[k]);
-      }
-    }
-    for (int s = 1; s < (1 << c.logl); s <<= 1) {  // the lanes that share a column
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], s);
-    }
-    const int col = v >> c.logl;
-    if ((v & ((1 << c.logl) - 1)) == 0 && col < c.fw) {
-#pragma unroll
-      for (int k = 0; k < CPL; ++k)
-        if (c.act[k]) pr_red_global(grow + (size_t)M::koff(k) * c.HW + col, t[k]);
-    }
-  }
-  __syncwarp();  // scratch is rewritten by the next flush
 }
 
-// Vertical pass: window of WIN footprint rows (rows cy .. cy+WIN-1) of U per channel pass; WIN >= the tallest band.
-template <int CPL, int WIN>
-__device__ __forceinline__ void pr_bwd_win(const PrBwdCtx<CPL>& c, const float* gp /* tile + slot/bin */,
-                                           const float* yrec) {
+// T[ph][col] = sum over the lane's bins of w * G[ph][bin], all CPL channel passes; lanes that share a column add up
+template <int CPL>
+__device__ __forceinline__ void pr_bwd_hrow(const PrBwdCol<CPL>& c, const float* grow, float (&t)[CPL]) {
   using M = PrMap<14, CPL>;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) t[k] = 0.f;
+  for (int i = 0; i < c.nps; ++i) {
+    const float w = c.wt[i];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) t[k] = fmaf(w, grow[M::koff(k) * 196 + i], t[k]);
+  }
+  for (int s = 1; s < (1 << c.logl); s <<= 1) {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], s);
+  }
+}
+
+// Window of WIN footprint rows (rows cy .. cy+WIN-1) of dF per channel pass; WIN >= the tallest band.
+template <int CPL, int WIN>
+__device__ __forceinline__ void pr_bwd_win(const PrBwdCol<CPL>& c, const float* yrec) {
   float acc[WIN][CPL];
 #pragma unroll
   for (int r = 0; r < WIN; ++r)
@@ -781,68 +760,61 @@ __device__ __forceinline__ void pr_bwd_win(const PrBwdCtx<CPL>& c, const float* 
     for (int k = 0; k < CPL; ++k) acc[r][k] = 0.f;
   int cy = 0;
   bool open = false;
-  auto advance = [&]() {  // row cy is complete
-    pr_bwd_flush<CPL>(c, cy, acc[0]);
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-#pragma unroll
-      for (int r = 0; r + 1 < WIN; ++r) acc[r][k] = acc[r + 1][k];
-      acc[WIN - 1][k] = 0.f;
-    }
-    ++cy;
-  };
+  const float* grow = c.gq;
 #pragma unroll 1
-  for (int ph = 0; ph < 14; ++ph, gp += 14) {
+  for (int ph = 0; ph < 14; ++ph, grow += 14) {
     const int4 ca = *reinterpret_cast<const int4*>(yrec + ph * 8);
     const float4 cb = *reinterpret_cast<const float4*>(yrec + ph * 8 + 4);
-    float g[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) g[k] = gp[M::koff(k) * 196];
-    if (ca.y > 0) {
-      if (!open) {
-        cy = ca.x;
-        open = true;
-      }
-      if (ca.x - cy > WIN) {  // (never with adaptive sampling) a gap: drain, restart at the new band
-        for (int r = 0; r < WIN; ++r) advance();
-        cy = ca.x;
-      }
-      while (cy < ca.x) advance();
-      float wy[WIN];
-      wy[0] = __int_as_float(ca.z);
-      wy[1] = __int_as_float(ca.w);
-      if (WIN > 2) wy[2] = cb.x;
-      if (WIN > 3) wy[WIN > 3 ? 3 : 0] = cb.y;
-      if (WIN > 4) wy[WIN > 4 ? 4 : 0] = cb.z;
-      if (WIN > 5) wy[WIN > 5 ? 5 : 0] = cb.w;
-#pragma unroll
-      for (int r = 0; r < WIN; ++r)
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) acc[r][k] = fmaf(wy[r], g[k], acc[r][k]);
+    if (ca.y <= 0) continue;
+    float t[CPL];
+    pr_bwd_hrow<CPL>(c, grow, t);
+    if (!open) {
+      cy = ca.x;
+      open = true;
     }
+    while (cy < ca.x) {  // row cy is complete (a gap of more than WIN rows just emits zero rows: never with
+      pr_bwd_red<CPL>(c, cy, acc[0]);  // adaptive sampling)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+#pragma unroll
+        for (int r = 0; r + 1 < WIN; ++r) acc[r][k] = acc[r + 1][k];
+        acc[WIN - 1][k] = 0.f;
+      }
+      ++cy;
+    }
+    float wy[WIN];
+    wy[0] = __int_as_float(ca.z);
+    wy[1] = __int_as_float(ca.w);
+    if (WIN > 2) wy[2] = cb.x;
+    if (WIN > 3) wy[WIN > 3 ? 3 : 0] = cb.y;
+#pragma unroll
+    for (int r = 0; r < WIN; ++r)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) acc[r][k] = fmaf(wy[r], t[k], acc[r][k]);
   }
-  if (open)
-    for (int r = 0; r < WIN; ++r) advance();
+  if (open) {
+#pragma unroll
+    for (int r = 0; r < WIN; ++r) pr_bwd_red<CPL>(c, cy + r, acc[r]);
+  }
 }
 
-// Bands taller than the window templates: every (output row, band row) pair is flushed on its own.
+// Bands taller than the window templates: every (output row, band row) pair is reduced on its own.
 template <int CPL>
-__device__ __forceinline__ void pr_bwd_gen(const PrBwdCtx<CPL>& c, const float* gp, const float* yrec,
-                                           const PrRecB* yrecB) {
-  using M = PrMap<14, CPL>;
+__device__ __forceinline__ void pr_bwd_gen(const PrBwdCol<CPL>& c, const float* yrec, const PrRecB* yrecB) {
+  const float* grow = c.gq;
 #pragma unroll 1
-  for (int ph = 0; ph < 14; ++ph, gp += 14) {
+  for (int ph = 0; ph < 14; ++ph, grow += 14) {
     const float* yr = yrec + ph * 8;
     const int ys = __float_as_int(yr[0]), ny = __float_as_int(yr[1]);
-    float g[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) g[k] = gp[M::koff(k) * 196];
+    if (ny <= 0) continue;
+    float t[CPL];
+    pr_bwd_hrow<CPL>(c, grow, t);
     for (int r = 0; r < ny; ++r) {
       const float wy = r < 6 ? yr[2 + r] : __ldg(&yrecB[ph].w[r - 6]);
       float u[CPL];
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) u[k] = wy * g[k];
-      pr_bwd_flush<CPL>(c, ys + r, u);
+      for (int k = 0; k < CPL; ++k) u[k] = wy * t[k];
+      pr_bwd_red<CPL>(c, ys + r, u);
     }
   }
 }
@@ -876,16 +848,11 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
   __syncwarp();
   uint32_t phase = 0;
   const int HW = H * W;
-  PrBwdCtx<CPL> ctx;
-  ctx.scratch = scr + warp * kPrScratch;
-  ctx.tbl = mytbl;
-  ctx.tpa = mytpa;
-  ctx.HW = HW;
-  ctx.W = W;
-  ctx.H = H;
-  ctx.slot = slot;
-  ctx.xi = lane & 15;
-  ctx.p = p;
+  PrBwdCol<CPL> col;
+  col.HW = HW;
+  col.W = W;
+  col.H = H;
+  const int xi = lane & 15;
   const int nunits = plan.counter[1] * ngroups;
   for (;;) {
     __syncthreads();
@@ -900,9 +867,9 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
     const PrChunk ck = plan.chunks[j];
     const int cbase = cg * CH, nch = min(CH, C - cbase), nroi = ck.end - ck.begin;
     const uint32_t tile_bytes = (uint32_t)nch * PER * 4u;
-    ctx.gimg = gin + ((size_t)ck.img * C + cbase + D * slot) * HW;
+    float* gimg = gin + ((size_t)ck.img * C + cbase + D * slot) * HW;  // this slot's first channel plane
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) ctx.act[k] = (M::koff(k) + D * slot) < nch && !(dbg & 1);
+    for (int k = 0; k < CPL; ++k) col.act[k] = (M::koff(k) + D * slot) < nch && !(dbg & 1);
     int i = 0;
     if (lane == 0) i = atomicAdd(&s_next, 1);
     i = __shfl_sync(0xffffffffu, i, 0);
@@ -937,11 +904,6 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
                         nv <= kPrTblV && nv * nps <= kPrTblFloats && nps <= P;
       if (band) {
         // ---- inverse of the x bands: for every (column, lane part) the contiguous bins whose band covers it ------
-        ctx.x0 = hd.x0;
-        ctx.fw = hd.fw;
-        ctx.nps = nps;
-        ctx.nv = nv;
-        ctx.logl = logl;
         const int shift_max = P - nps;  // windows of nps bins are shifted left to stay inside 0..13
         for (int v = lane; v < nv; v += 32) {
           float* wt = mytbl + v * nps;
@@ -970,9 +932,18 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
       __syncwarp();
       const float* gp = tile + (D * slot) * PER + p;
       if (band) {
-        if (hd.nymax <= 2) pr_bwd_win<CPL, 2>(ctx, gp, yrec);
-        else if (hd.nymax <= 4) pr_bwd_win<CPL, 4>(ctx, gp, yrec);
-        else pr_bwd_gen<CPL>(ctx, gp, yrec, blkB + 15);
+        col.nps = nps;
+        col.logl = logl;
+        for (int v = xi; v < nv; v += 16) {  // 16 columns (or column parts) per pass, the same for both slots
+          const int cc = v >> logl;
+          col.gq = tile + (D * slot) * PER + mytpa[v];
+          col.wt = mytbl + v * nps;
+          col.gcol = gimg + hd.x0 + cc;
+          col.red = (v & ((1 << logl) - 1)) == 0 && cc < hd.fw;
+          if (hd.nymax <= 2) pr_bwd_win<CPL, 2>(col, yrec);
+          else if (hd.nymax <= 4) pr_bwd_win<CPL, 4>(col, yrec);
+          else pr_bwd_gen<CPL>(col, yrec, blkB + 15);
+        }
       } else if (hd.cls == PR_DIRECT || (hd.cls == PR_BAND && !(dbg & 6))) {
         // ---- per-sample scatter in the reference's order (sparse / huge sampling grids): rare ------------------
         const RoiGeom g = roi_geom(rois + (size_t)hd.roi * 5, scale, aligned, P, P, sampling_ratio, H, W);
@@ -990,8 +961,8 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
                 if (tx.wl == 0.f && tx.wh == 0.f) continue;
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
-                  if (!ctx.act[k]) continue;
-                  float* b = ctx.gimg + (size_t)M::koff(k) * HW;
+                  if (!col.act[k]) continue;
+                  float* b = gimg + (size_t)M::koff(k) * HW;
                   pr_red_global(b + ty.lo * W + tx.lo, go[k] * ty.wl * tx.wl);
                   pr_red_global(b + ty.lo * W + tx.hi, go[k] * ty.wl * tx.wh);
                   pr_red_global(b + ty.hi * W + tx.lo, go[k] * ty.wh * tx.wl);
