@@ -5,11 +5,11 @@ from .fast_rcnn import FastRCNNOutputLayers, fast_rcnn_inference, fast_rcnn_infe
 from .gather import GatherLayer
 from .matcher import Matcher, pairwise_iou
 from .poolers import ROIPooler, convert_boxes_to_pooler_format
-from .proposal_utils import find_top_rpn_proposals
+from .proposal_utils import decode_proposals, find_top_rpn_proposals, predict_proposals
 from .roi_heads import CLIPRes5ROIHeads, ROIHeads, add_ground_truth_to_proposals, label_and_sample_proposals
 from .sampling import subsample_labels
 
 __all__ = ["Box2BoxTransform", "caption_consistency_loss", "image_caption_consistency_loss", "kd_l1_loss",
            "FastRCNNOutputLayers", "fast_rcnn_inference", "fast_rcnn_inference_single_image", "GatherLayer",
-           "ROIPooler", "convert_boxes_to_pooler_format", "find_top_rpn_proposals", "Matcher", "pairwise_iou", "ROIHeads", "CLIPRes5ROIHeads", "label_and_sample_proposals",
+           "ROIPooler", "convert_boxes_to_pooler_format", "find_top_rpn_proposals", "predict_proposals", "decode_proposals", "Matcher", "pairwise_iou", "ROIHeads", "CLIPRes5ROIHeads", "label_and_sample_proposals",
            "add_ground_truth_to_proposals", "subsample_labels"]

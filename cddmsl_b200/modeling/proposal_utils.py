@@ -13,6 +13,7 @@ from typing import List, Tuple
 import torch
 
 from ..layers import batched_nms, batched_nms_images, cat
+from .. import ops
 from ..structures import Boxes, Instances
 
 # The container types the results are built with.  When `find_top_rpn_proposals` is patched into the reference's
@@ -110,5 +111,59 @@ def find_top_rpn_proposals(proposals: List[torch.Tensor], pred_objectness_logits
         res = CONTAINERS["Instances"](image_size)
         res.proposal_boxes = boxes[keep]
         res.objectness_logits = scores_per_img[keep]
+        results.append(res)
+    return results
+
+
+def decode_proposals(anchors: List, pred_anchor_deltas: List[torch.Tensor], box2box_transform) -> List[torch.Tensor]:
+    """`RPN._decode_proposals` (proposal_generator/rpn.py:514-533): anchors (one `Boxes` per level, shared by the
+    images) + predicted deltas [N, Hi*Wi*A, B] -> proposals [N, Hi*Wi*A, B] per level."""
+    n = pred_anchor_deltas[0].shape[0]
+    proposals = []
+    for anchors_i, deltas_i in zip(anchors, pred_anchor_deltas):
+        a = anchors_i.tensor if hasattr(anchors_i, "tensor") else anchors_i
+        b = a.size(1)
+        deltas_i = deltas_i.reshape(-1, b)
+        a = a.unsqueeze(0).expand(n, -1, -1).reshape(-1, b)
+        proposals.append(box2box_transform.apply_deltas(deltas_i, a).view(n, -1, b))
+    return proposals
+
+
+@torch.no_grad()
+def predict_proposals(anchors: List, pred_objectness_logits: List[torch.Tensor], pred_anchor_deltas: List[torch.Tensor],
+                      image_sizes: List[Tuple[int, int]], *, box2box_transform, nms_thresh: float, pre_nms_topk: int,
+                      post_nms_topk: int, min_box_size: float, training: bool):
+    """`RPN.predict_proposals` (proposal_generator/rpn.py:482-512): decode, top-k, clip, drop empty boxes, NMS,
+    post-NMS top-k; a list of N Instances (`proposal_boxes`, `objectness_logits`, score-descending).
+
+    One RPN level on CUDA (the C4 detector of both CDDMSL configs): `sort` (the segmented top-k) -> ONE kernel for
+    decode + finite flag + clip + non-empty + stable compaction of the top-k candidates of every image
+    (csrc/rpn_decode.cu; only the kept candidates are decoded) -> ONE batched NMS call -> ONE device->host read
+    (kept counts + finite flag).  Several levels / CPU tensors: the reference-shaped path."""
+    single = len(pred_objectness_logits) == 1 and pred_objectness_logits[0].is_cuda and BATCHED_IMAGES
+    if not single or len(image_sizes) == 0 or len(box2box_transform.weights) != 4:
+        props = decode_proposals(anchors, pred_anchor_deltas, box2box_transform)
+        return find_top_rpn_proposals(props, pred_objectness_logits, image_sizes, nms_thresh, pre_nms_topk,
+                                      post_nms_topk, min_box_size, training)
+    logits = pred_objectness_logits[0]
+    n, a_tot = logits.shape
+    k = min(a_tot, pre_nms_topk)
+    sorted_logits, idx = logits.sort(descending=True, dim=1)        # proposal_utils.py:77-79
+    topk_scores, topk_idx = sorted_logits.narrow(1, 0, k), idx.narrow(1, 0, k)
+    an = anchors[0].tensor if hasattr(anchors[0], "tensor") else anchors[0]
+    hw = torch.tensor([[float(h), float(w)] for h, w in image_sizes], device=logits.device)
+    boxes, scores, counts, fin = ops.rpn_decode_topk(an, pred_anchor_deltas[0].reshape(n, a_tot, 4), topk_idx,
+                                                     topk_scores, hw, [float(v) for v in box2box_transform.weights],
+                                                     float(box2box_transform.scale_clamp), float(min_box_size))
+    keep, num_keep = batched_nms_images(boxes, scores, None, counts, nms_thresh)
+    host = torch.cat([num_keep.to(torch.int32), fin]).tolist()       # the one sync of the batch
+    if training and not host[-1]:
+        raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+    results = []
+    for i, image_size in enumerate(image_sizes):
+        kk = keep[i, : min(int(host[i]), post_nms_topk)]
+        res = CONTAINERS["Instances"](image_size)
+        res.proposal_boxes = CONTAINERS["Boxes"](boxes[i][kk])
+        res.objectness_logits = scores[i][kk]
         results.append(res)
     return results

@@ -495,6 +495,40 @@ def _(packed_all, norms_local, rank, grad_scale, want_grads):
     return packed_all.new_empty(()), packed_all.new_empty(shape), packed_all.new_empty(shape)
 
 
+# ------------------------------------------------------------------------------------------ RPN decode
+@torch.library.custom_op("cddmsl_b200::rpn_decode_topk", mutates_args=(), device_types="cuda")
+def rpn_decode_topk(anchors: Tensor, deltas: Tensor, topk_idx: Tensor, topk_scores: Tensor, image_hw: Tensor,
+                    weights: List[float], scale_clamp: float,
+                    min_box_size: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """rpn.py:514-533 + box_regression.py:77-117 + proposal_utils.py:95-114 for a batch (csrc/rpn_decode.cu).
+    Returns (boxes [N,K,4], scores [N,K] -- survivors first, score order --, counts int32 [N], all_finite int32 [1])."""
+    _lib.require_cuda(deltas, "deltas")
+    an, dl = _f32c(anchors), _f32c(deltas)
+    idx = topk_idx.to(torch.int64).contiguous()
+    sc, hw = _f32c(topk_scores), _f32c(image_hw)
+    n, a = dl.shape[0], an.shape[0]
+    k = idx.shape[1]
+    dev = dl.device
+    boxes = torch.empty((n, k, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((n, k), dtype=torch.float32, device=dev)
+    counts = torch.empty((n,), dtype=torch.int32, device=dev)
+    fin = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cddmsl_rpn_decode_topk(_lib.ptr(an), _lib.ptr(dl), _lib.ptr(idx), _lib.ptr(sc), _lib.ptr(hw),
+                                                     n, a, k, float(weights[0]), float(weights[1]), float(weights[2]),
+                                                     float(weights[3]), float(scale_clamp), float(min_box_size),
+                                                     _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(counts), _lib.ptr(fin),
+                                                     _lib.stream_ptr(dev)), "rpn_decode_topk")
+    return boxes, scores, counts, fin
+
+
+@rpn_decode_topk.register_fake
+def _(anchors, deltas, topk_idx, topk_scores, image_hw, weights, scale_clamp, min_box_size):
+    n, k = topk_idx.shape
+    return (deltas.new_empty((n, k, 4)), deltas.new_empty((n, k)), deltas.new_empty((n,), dtype=torch.int32),
+            deltas.new_empty((1,), dtype=torch.int32))
+
+
 # ------------------------------------------------------------------------------------------ KD regulariser
 @torch.library.custom_op("cddmsl_b200::kd_l1", mutates_args=(), device_types="cuda")
 def kd_l1(teacher: Tensor, student: Tensor, want_grad: bool) -> Tuple[Tensor, Tensor]:

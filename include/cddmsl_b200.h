@@ -91,6 +91,18 @@ int cddmsl_nms_batched(const float* boxes, const float* scores, const int64_t* i
                        int64_t Mmax, double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep,
                        void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
 
+/* Proposal pre-processing between the RPN head and NMS for a batch: RPN._decode_proposals
+ * (proposal_generator/rpn.py:514-533) = Box2BoxTransform.apply_deltas (box_regression.py:77-117) on the pre-NMS
+ * top-k candidates of every image, then the finite check, Boxes.clip, Boxes.nonempty and the boolean selection of
+ * proposal_utils.py:95-114 as a stable compaction.  anchors [A,4], deltas [N,A,4], topk_idx int64 [N,K] (anchor
+ * indices in descending score order), topk_scores [N,K], image_hw [N,2] = (h, w).  Out: boxes_out [N,K,4] /
+ * scores_out [N,K] with the survivors first, in score order; counts int32 [N]; *all_finite = 0 if any decoded box or
+ * score of the batch is Inf/NaN (the reference raises FloatingPointError in training).  Feeds cddmsl_nms_batched. */
+int cddmsl_rpn_decode_topk(const float* anchors, const float* deltas, const int64_t* topk_idx,
+                           const float* topk_scores, const float* image_hw, int N, int64_t A, int K, float wx,
+                           float wy, float ww, float wh, float scale_clamp, float min_box_size, float* boxes_out,
+                           float* scores_out, int32_t* counts, int32_t* all_finite, cddmsl_stream_t stream);
+
 /* ---------------------------------------------------------------- piece 3: CLIP box predictor --- */
 /* loss modes */
 enum { CDDMSL_LOSS_FOCAL = 0, CDDMSL_LOSS_CE = 1, CDDMSL_LOSS_WEIGHTED_CE = 2 };

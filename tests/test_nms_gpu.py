@@ -212,3 +212,55 @@ def test_find_top_rpn_proposals_batched_equals_loop():
         assert torch.equal(rb.proposal_boxes.tensor, rl.proposal_boxes.tensor)
         assert torch.equal(rb.objectness_logits, rl.objectness_logits)
         assert len(rb.objectness_logits) > 0
+
+
+@pytest.mark.parametrize("hw_feat,img", [((38, 63), (600, 1000)), ((64, 128), (1024, 2048))])
+def test_predict_proposals_fused_decode(hw_feat, img):
+    """rpn.py:482-533 + box_regression.py:77-117 + proposal_utils.py:95-130 on 35 910 / 122 880 anchors per image:
+    the fused decode + clip + non-empty + compaction kernel in front of the batched NMS against (a) the
+    reference-shaped sequence of torch ops on the same device -- bit-exact -- and (b) the CPU oracle."""
+    import cddmsl_b200.modeling.proposal_utils as pu
+    from cddmsl_b200.modeling import Box2BoxTransform, predict_proposals
+    from oracle import torch_ref
+
+    g = synth.generator(91)
+    n_img, na = 3, hw_feat[0] * hw_feat[1] * 15
+    # anchors: 15 per location (3 ratios x 5 sizes) around the cell centres, some hanging over the border
+    ys, xs = torch.meshgrid(torch.arange(hw_feat[0]) * 16.0, torch.arange(hw_feat[1]) * 16.0, indexing="ij")
+    ctr = torch.stack([xs, ys, xs, ys], -1).reshape(-1, 1, 4)
+    sizes = torch.tensor([32.0, 64.0, 128.0, 256.0, 512.0])
+    ratios = torch.tensor([0.5, 1.0, 2.0])
+    w_ = (sizes[None, :] / ratios[:, None].sqrt()).reshape(-1)
+    h_ = (sizes[None, :] * ratios[:, None].sqrt()).reshape(-1)
+    cell = torch.stack([-w_ / 2, -h_ / 2, w_ / 2, h_ / 2], -1)[None]
+    anchors = (ctr + cell).reshape(-1, 4).contiguous()
+    assert anchors.shape[0] == na
+    deltas = torch.randn(n_img, na, 4, generator=g) * torch.tensor([1.0, 1.0, 2.0, 2.0])
+    deltas[0, :50, 2] = 40.0                       # beyond the scale clamp
+    logits = torch.randn(n_img, na, generator=g)
+    b2b = Box2BoxTransform((1.0, 1.0, 1.0, 1.0))
+    args = dict(box2box_transform=b2b, nms_thresh=0.7, pre_nms_topk=12000, post_nms_topk=2000, min_box_size=0.0,
+                training=True)
+    fused = predict_proposals([anchors.to(DEV)], [logits.to(DEV)], [deltas.to(DEV)], [img] * n_img, **args)
+    props = pu.decode_proposals([anchors.to(DEV)], [deltas.to(DEV)], b2b)
+    eager = pu.find_top_rpn_proposals(props, [logits.to(DEV)], [img] * n_img, 0.7, 12000, 2000, 0.0, True)
+    for f, e in zip(fused, eager):
+        assert torch.equal(f.proposal_boxes.tensor, e.proposal_boxes.tensor)
+        assert torch.equal(f.objectness_logits, e.objectness_logits)
+    # CPU oracle (torch CPU exp may differ from the device's by an ulp: boxes to 1e-5, same kept count +- borderline)
+    cpu_props = pu.decode_proposals([anchors], [deltas], b2b)[0]
+    for i in range(n_img):
+        lg, idx = logits[i].sort(descending=True)
+        wb, ws = torch_ref.find_top_rpn_proposals_single_image(cpu_props[i][idx[:12000]], lg[:12000], img, 0.7, 2000)
+        gb = fused[i].proposal_boxes.tensor.cpu()
+        assert abs(len(gb) - len(wb)) <= 2
+        m = min(len(gb), len(wb), 200)            # the head of the list is far from any tie
+        assert torch.allclose(gb[:m], wb[:m], rtol=1e-5, atol=1e-3)
+        assert torch.equal(fused[i].objectness_logits.cpu()[:m], ws[:m])
+    bad = deltas.clone()
+    bad[1, int(logits[1].argmax()), 0] = float("nan")
+    with pytest.raises(FloatingPointError):
+        predict_proposals([anchors.to(DEV)], [logits.to(DEV)], [bad.to(DEV)], [img] * n_img, **args)
+    args["training"] = False                      # inference: the non-finite candidate is dropped silently
+    out = predict_proposals([anchors.to(DEV)], [logits.to(DEV)], [bad.to(DEV)], [img] * n_img, **args)
+    assert torch.isfinite(out[1].proposal_boxes.tensor).all()
