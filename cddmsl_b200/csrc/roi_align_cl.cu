@@ -1083,6 +1083,7 @@ static int launch_bwd_cl(const float* gout, const float* rois, float* gt, int N,
 // Measured (cfg #2): forward 2.66 -> 2.52 ms; backward 2.57 -> 3.33 ms (sixty-four 112-byte row fetches per box cost
 // more than the barrier they remove) -- so the default enables the forward only.
 int g_roi_tma = 1;
+constexpr int kTmaEncodeFailed = -1000;  // internal: cuTensorMapEncodeTiled unavailable / failed -> non-TMA kernels
 
 static bool roi_tma_ok(int C, int R, int P, int bit) {
   return (g_roi_tma & bit) && P == 14 && C % 64 == 0 && (long long)R * C < 0x7fffffffLL;
@@ -1094,7 +1095,7 @@ static int launch_fwd_cl_tma(const float* ft, const float* in, const float* rois
   CUtensorMap map;
   if (tma_encode_2d_f32(&map, out, P * P, (unsigned long long)R * C, P * P * 4, kRowsPerWarp * P, 32 * CPL,
                         CU_TENSOR_MAP_SWIZZLE_NONE))
-    return CDDMSL_EINVAL;
+    return kTmaEncodeFailed;
   const int gpc = max(1, g_roi_gpc);
   const int ngroups = ceil_div(C, 32 * CPL * gpc);
   if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
@@ -1114,7 +1115,7 @@ static int launch_bwd_cl_tma(const float* gout, const float* rois, float* gt, in
   CUtensorMap map;
   if (tma_encode_2d_f32(&map, gout, P * P, (unsigned long long)R * C, P * P * 4, kRowsPerWarp * P, 32 * CPL,
                         CU_TENSOR_MAP_SWIZZLE_NONE))
-    return CDDMSL_EINVAL;
+    return kTmaEncodeFailed;
   const int gpc = max(1, g_roi_gpc);
   const int ngroups = ceil_div(C, 32 * CPL * gpc);
   if ((long long)R * ngroups > 0x7fffffffLL) return CDDMSL_EINVAL;
@@ -1132,8 +1133,10 @@ int roi_align_fwd_cl(const float* in, const float* rois, float* out, int N, int 
                      float scale, int sampling_ratio, int aligned, float* ft, cudaStream_t stream) {
   int rc = launch_transpose(in, ft, N, C, H * W, stream);  // NCHW -> NHWC
   if (rc) return rc;
-  if (R > 0 && roi_tma_ok(C, R, P, 1) && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
-    return launch_fwd_cl_tma(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
+  if (R > 0 && roi_tma_ok(C, R, P, 1) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    rc = launch_fwd_cl_tma(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
+    if (rc != kTmaEncodeFailed) return rc;  // no tensor map: the bulk-store kernels handle the same shapes
+  }
   if (P == 7) return launch_fwd_cl<7, 2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
   return g_fwd_cpl == 2 ? launch_fwd_cl<14, 2>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
                         : launch_fwd_cl<14, 1>(ft, in, rois, out, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
@@ -1143,9 +1146,11 @@ int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, in
                      float scale, int sampling_ratio, int aligned, float* gt, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(gt, 0, (size_t)N * C * H * W * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
-  int rc = (R > 0 && roi_tma_ok(C, R, P, 2) && (reinterpret_cast<uintptr_t>(gout) & 15) == 0)
-               ? launch_bwd_cl_tma(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
-           : P == 7 ? launch_bwd_cl<7, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
+  int rc = kTmaEncodeFailed;
+  if (R > 0 && roi_tma_ok(C, R, P, 2) && (reinterpret_cast<uintptr_t>(gout) & 15) == 0)
+    rc = launch_bwd_cl_tma(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream);
+  if (rc == kTmaEncodeFailed)
+    rc = P == 7 ? launch_bwd_cl<7, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
            : g_bwd_cpl == 2
                ? launch_bwd_cl<14, 2>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream)
                : launch_bwd_cl<14, 1>(gout, rois, gt, N, C, H, W, R, scale, sampling_ratio, aligned, stream);

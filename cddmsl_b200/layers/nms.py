@@ -1,10 +1,11 @@
 """`batched_nms` / `nms` with the reference's signatures (detectron2/layers/nms.py:19-39 and the
 re-exported `torchvision.ops.nms`), backed by csrc/nms.cu.
 
-Mode selection mirrors what the reference's call chain does on the oracle's device (CPU):
+Mode selection mirrors what the reference's call chain does ON A GPU (where it trains):
 `len(boxes) < 40000` -> torchvision `batched_nms`, which applies the coordinate-offset trick when
 `boxes.numel() <= COORD_TRICK_NUMEL_LIMIT` and the per-class loop otherwise (torchvision/ops/boxes.py:80-83:
-4000 on CPU, 100000 on CUDA); `>= 40000` -> detectron2's own per-class loop.  Both branches that loop over
+100000 on CUDA, 4000 on CPU -- the oracle tests set the CPU rule explicitly to compare with the CPU oracle);
+`>= 40000` -> detectron2's own per-class loop.  Both branches that loop over
 classes are the same function of the inputs and map to the class-aware kernel (`coord_trick=False`).
 Kept indices come back ordered by score (descending), ties by ascending index — the order of `nms` itself;
 the reference's per-class branches re-sort with an unstable sort, so among *exactly equal* scores their
@@ -16,8 +17,8 @@ import torch
 
 from .. import ops
 
-# torchvision's CPU rule (the oracle's).  Set to 100_000 to mirror torchvision's CUDA rule instead.
-COORD_TRICK_NUMEL_LIMIT = 4000
+# torchvision's CUDA rule (what the reference's training runs); 4000 is its CPU rule (set by the oracle tests).
+COORD_TRICK_NUMEL_LIMIT = 100_000
 
 
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:

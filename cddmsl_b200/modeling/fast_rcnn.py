@@ -293,6 +293,7 @@ class FastRCNNOutputLayers(nn.Module):
                  and gt_classes.numel() == scores.shape[0] and scores.is_cuda)
         if fused:
             _, x, w = self._last
+            self._last = None   # do not keep x (and its graph) alive until the next forward
             mode, gamma, bgw = self._loss_mode()
             # when x will need its gradient it is produced by the same pass (the op keeps it for backward)
             loss_cls, _, _, counters = ops.clip_head_loss(x, w, self.cls_bg_score.weight,

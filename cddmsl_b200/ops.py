@@ -318,8 +318,17 @@ def _(x, weight, bg_weight, dscores, temperature):
     return torch.empty_like(x)
 
 
+def _frozen_embeddings(weight, bg_weight):
+    """The reference freezes the concept and background embeddings (fast_rcnn.py:453, :461); the fused backward only
+    produces d/dx.  Unfrozen embeddings would silently train on zero gradients: refuse instead."""
+    if weight.requires_grad or bg_weight.requires_grad:
+        raise RuntimeError("cddmsl_b200 CLIP head: the concept / background embeddings must be frozen "
+                           "(requires_grad=False, as in the reference); no gradient is computed for them")
+
+
 def _scores_setup(ctx, inputs, output):
     x, weight, bg_weight, temperature = inputs
+    _frozen_embeddings(weight, bg_weight)
     ctx.save_for_backward(x, weight, bg_weight)
     ctx.temperature = temperature
 
@@ -371,6 +380,9 @@ def _(x, weight, bg_weight, gt, temperature, loss_mode, gamma, bg_cls_weight, gr
 
 def _loss_setup(ctx, inputs, output):
     x, weight, bg_weight, gt, temperature, loss_mode, gamma, bg_cls_weight, gs, strict_nan, _ws_, want_dx = inputs
+    _frozen_embeddings(weight, bg_weight)
+    # only `loss` is differentiable: the optional scores / dx / counters are side products of the same pass
+    ctx.mark_non_differentiable(output[1], output[2], output[3])
     ctx.have_dx = bool(want_dx) and gs is None
     if ctx.have_dx:
         ctx.save_for_backward(output[2])  # d loss / d x for a unit upstream gradient, produced by the forward pass

@@ -25,3 +25,16 @@ def _built_oracle():
 
     c_ref.build()
     yield
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _cpu_oracle_nms_rule():
+    """The NMS fixtures come from the CPU oracle, where torchvision switches from the coordinate-offset trick to the
+    per-class loop at numel > 4000 (100 000 on CUDA, the product's default): compare like with like."""
+    import importlib
+
+    lnms = importlib.import_module("cddmsl_b200.layers.nms")
+    old = lnms.COORD_TRICK_NUMEL_LIMIT
+    lnms.COORD_TRICK_NUMEL_LIMIT = 4000
+    yield
+    lnms.COORD_TRICK_NUMEL_LIMIT = old
