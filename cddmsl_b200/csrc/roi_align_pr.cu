@@ -60,6 +60,14 @@ constexpr int kPrBlockBytes = kPrBlockSlots * 32;   // A half: 928 bytes
 constexpr int kPrBlockVec = kPrBlockBytes / 16;     // 58 16-byte pieces
 constexpr int kPrBlockFloats = kPrBlockBytes / 4;   // 232
 
+// Inverse x table of the backward (per RoI, kPrInvBytes): for every footprint column (or column part, when several
+// lanes share a column of a narrow footprint) the contiguous window of bins whose band covers it and their weights.
+//   fmt 1 (fw <= 16): 16 entries of 32 bytes {int first_bin; float w[7]}, 2^logl lanes per column, nps bins per lane
+//   fmt 2 (fw <= 128, at most 3 bins per column): fw entries of 16 bytes {int first_bin; float w[3]}
+// hdr.pad = fmt | logl << 8 | nps << 16 (fmt 0: no table -> per-sample path).
+constexpr int kPrInvBytes = 2048, kPrInvFloats = kPrInvBytes / 4;
+constexpr int kPrInvPrefetch = 1024;  // bytes fetched ahead for every RoI (all of fmt 1, fmt 2 up to 64 columns)
+
 struct __align__(16) PrChunk {
   int img, begin, end, pad;
 };
@@ -71,6 +79,7 @@ struct PrPlan {
   PrChunk* chunks;
   PrRecA* blocksA;  // [R][29]
   PrRecB* blocksB;  // [R][29]
+  float* inv;       // [R][kPrInvFloats]: inverse x tables of the backward (NULL: not wanted)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -173,6 +182,7 @@ __global__ void __launch_bounds__(1024) pr_plan_scan_kernel(PrPlan plan, int N, 
 template <int P>
 __global__ void __launch_bounds__(256) pr_plan_fill_kernel(const float* __restrict__ rois, int R, int N, int H, int W,
                                                            float scale, int sampling_ratio, int aligned, PrPlan plan) {
+  static_assert(P <= 14, "two bins axes in one warp");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= R) return;
@@ -272,6 +282,51 @@ __global__ void __launch_bounds__(256) pr_plan_fill_kernel(const float* __restri
     h.pad = 0;
     *reinterpret_cast<PrHdr*>(blkA) = h;
   }
+  // ---- inverse x table for the backward ------------------------------------------------------------------------
+  if (!plan.inv || !valid || !mergeable || ovf || x1 <= 0) return;
+  const int fw = x1 - x0;
+  int fmt = 0, logl = 0, nps = 0;
+  if (fw <= 16) {
+    logl = fw <= 2 ? 3 : fw <= 4 ? 2 : fw <= 8 ? 1 : 0;
+    nps = (ni + (1 << logl) - 1) >> logl;
+    fmt = (nps >= 1 && nps <= 7) ? 1 : 0;
+  } else if (fw <= 128 && ni <= 3) {
+    fmt = 2;
+    nps = ni;
+  }
+  if (!fmt) return;
+  __syncwarp();  // the x records written above are read back by other lanes
+  float* inv = plan.inv + (size_t)pos * kPrInvFloats;
+  const int nv = fmt == 1 ? 16 : fw, esz = fmt == 1 ? 8 : 4, wmax = esz - 1;
+  for (int v = lane; v < nv; v += 32) {
+    const int col = v >> logl, part = v & ((1 << logl) - 1);
+    float w[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) w[q] = 0.f;
+    int pa = -1, seen = 0;
+    if (col < fw) {
+      const int x = x0 + col;
+      for (int pw = 0; pw < P; ++pw) {
+        const int xs = blkA[1 + pw].start, nn = blkA[1 + pw].n;
+        const int jx = x - xs;
+        if (jx >= 0 && jx < nn) {
+          if (seen >= part * nps && seen < (part + 1) * nps) {
+            if (pa < 0) pa = min(pw, P - nps);
+            const float wv = jx < 6 ? blkA[1 + pw].w[jx] : blkB[1 + pw].w[jx - 6];
+            const int q = pw - pa;
+#pragma unroll
+            for (int qq = 0; qq < 7; ++qq)
+              if (qq == q) w[qq] = wv;
+          }
+          ++seen;
+        }
+      }
+    }
+    float* e = inv + v * esz;
+    e[0] = __int_as_float(pa < 0 ? 0 : pa);
+    for (int q = 0; q < wmax; ++q) e[1 + q] = w[q];
+  }
+  if (lane == 31) reinterpret_cast<PrHdr*>(blkA)->pad = fmt | (logl << 8) | (nps << 16);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -665,21 +720,19 @@ roi_align_fwd_pr_kernel(const float* __restrict__ in, const float* __restrict__ 
 // backward
 // ------------------------------------------------------------------------------------------------
 // Transpose of the forward.  Global traffic: the compulsory stream of the pooled gradient (one 1-D bulk load of the
-// RoI's contiguous [CH][196] tile per visit, mbarrier completion) and ONE coalesced red.global.add per (footprint
-// row, channel) into the zeroed NCHW gradient map -- fh*fw reductions per RoI and channel, all of them 64-byte
-// runs on an L2-resident image (the round-1 kernel issued ~(fh+14)*fw and moved 12 GB through the L2 atomic units).
-// Per RoI a warp
+// RoI's contiguous [CH][196] tile per visit, mbarrier completion, fetched one RoI ahead) and ONE coalesced
+// red.global.add per (footprint row, channel) into the zeroed NCHW gradient map: fh*fw reductions per RoI and
+// channel in 64-byte runs on an L2-resident image (the round-1 kernel issues ~(fh+14)*fw and moves 12 GB through the
+// L2 atomic units).  Per RoI a warp
 //   1. accumulates U = Ay^T G in registers with the lanes on the BINS (the y bands are warp-uniform): a window of WIN
 //      footprint rows per channel pass; a row leaves the window complete;
-//   2. transposes the completed row so that the lanes are on the footprint COLUMNS: the 4 channel passes of a bin go
-//      to a scratch line as one float4, and lane (column x) sums w * u4 over the bins whose band covers x -- the
-//      inverse of the x bands, built once per visit into a small per-warp table.  Narrow footprints (most RoIs are
-//      only a few cells wide, so a column is shared by up to 14 bins) split a column's bins over 2-8 lanes and finish
-//      with a shuffle reduction; wide footprints take several 16-column passes.
+//   2. transposes the completed row: the 4 channel passes of a bin go to a 16-entry scratch line as one float4, and
+//      lane (column x) sums w * u4 over the contiguous window of bins whose band covers x.  The windows come from the
+//      INVERSE x table the planning kernel built (pr_plan_fill_kernel) and the warp prefetched with cp.async; narrow
+//      footprints (most RoIs are a few cells wide, so a column is shared by up to 14 bins) use 2-8 lanes per column
+//      and a shuffle reduction, wide ones take several 16-column passes.
 constexpr int kPrBwdWarps = 16;
 constexpr int kPrBwdThreads = kPrBwdWarps * 32;
-constexpr int kPrTblV = 144;                      // virtual columns (lane slots) the inverse table holds
-constexpr int kPrTblFloats = 576;                 // weights: nv * nps <= 576 (16 x 14 narrow, 129 x 4 wide)
 constexpr int kPrScratch = 2 * 16 * 4;            // [SLOTS][16 bins][4 passes]
 
 __device__ __forceinline__ void pr_mbar_init(uint64_t* bar) {
@@ -711,48 +764,104 @@ __device__ __forceinline__ void pr_red_global(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// Per-lane state of one 16-column pass: the lane owns (part of) footprint column `col`.
-template <int CPL>
-struct PrBwdCol {
-  const float* gq;   // grad tile + slot's first channel + first bin of this lane's window of bins
-  const float* wt;   // [nps] weights of those bins for this column (shared memory)
-  float* gcol;       // gin + slot's first channel plane + x0 + col
-  int nps, logl, HW, W, H;
-  bool red;          // this lane writes the column (first lane of the column, column inside the footprint)
-  bool act[CPL];     // channel pass exists (ragged last group)
+// Per-warp state of the transposed (horizontal) pass of one visit.
+struct PrBwdFlush {
+  float* sline;        // this slot's scratch line [16 bins][4 passes]
+  const float* inv;    // the RoI's inverse table (shared memory)
+  char* grow;          // gin + slot's first channel plane + row cy + x0 + this lane's column (bytes; advanced per row)
+  int fmt, logl, nps, npass, fw;
+  unsigned hw4, w4;    // bytes between channel planes / rows of gin
+  int xi, p;
+  bool red0;           // fmt 1: this lane is the first lane of a column inside the footprint
+  // fmt 1: the lane's window of bins, fixed for the visit
+  const float* sc1;    // sline + first_bin * 4
+  float w1[7];
 };
 
 template <int CPL>
-__device__ __forceinline__ void pr_bwd_red(const PrBwdCol<CPL>& c, int y, const float (&u)[CPL]) {
+__device__ __forceinline__ void pr_red4(char* g, unsigned hw4, const float (&t)[CPL], const bool (&act)[CPL]) {
   using M = PrMap<14, CPL>;
-  if (c.red && y >= 0 && y < c.H) {  // rows beyond the map only ever collect zero weights
-    float* g = c.gcol + (size_t)y * c.W;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k)
-      if (c.act[k]) pr_red_global(g + (size_t)M::koff(k) * c.HW, u[k]);
-  }
+  for (int k = 0; k < CPL; ++k)
+    if (act[k]) pr_red_global(reinterpret_cast<float*>(g + (size_t)M::koff(k) * hw4), t[k]);
 }
 
-// T[ph][col] = sum over the lane's bins of w * G[ph][bin], all CPL channel passes; lanes that share a column add up
+// Row cy of U is complete: gin[cy][x0 + col] += sum over the column's bins; then the row pointer moves on.
 template <int CPL>
-__device__ __forceinline__ void pr_bwd_hrow(const PrBwdCol<CPL>& c, const float* grow, float (&t)[CPL]) {
-  using M = PrMap<14, CPL>;
+__device__ __forceinline__ void pr_bwd_flush(PrBwdFlush& f, bool in_map, const float (&u)[CPL],
+                                             const bool (&act)[CPL]) {
+  if (in_map) {  // rows beyond the map only ever collect zero weights
+    if (CPL == 4) {
+      *reinterpret_cast<float4*>(f.sline + f.p * 4) = make_float4(u[0], u[1 % CPL], u[2 % CPL], u[3 % CPL]);
+    } else {
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) t[k] = 0.f;
-  for (int i = 0; i < c.nps; ++i) {
-    const float w = c.wt[i];
+      for (int k = 0; k < CPL; ++k) f.sline[f.p * 4 + k] = u[k];
+    }
+    __syncwarp();
+    if (f.fmt == 1) {
+      float t[CPL];
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) t[k] = fmaf(w, grow[M::koff(k) * 196 + i], t[k]);
+      for (int k = 0; k < CPL; ++k) t[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        if (i < f.nps) {  // warp-uniform
+          if (CPL == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(f.sc1 + 4 * i);
+            t[0] = fmaf(f.w1[i], q.x, t[0]);
+            t[1 % CPL] = fmaf(f.w1[i], q.y, t[1 % CPL]);
+            t[2 % CPL] = fmaf(f.w1[i], q.z, t[2 % CPL]);
+            t[3 % CPL] = fmaf(f.w1[i], q.w, t[3 % CPL]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) t[k] = fmaf(f.w1[i], f.sc1[4 * i + k], t[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (s < f.logl) {  // the lanes that share a column
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], 1 << s);
+        }
+      }
+      if (f.red0) pr_red4<CPL>(f.grow, f.hw4, t, act);
+    } else {
+      for (int ps = 0; ps < f.npass; ++ps) {
+        const int v = f.xi + 16 * ps;
+        const float4 e = *reinterpret_cast<const float4*>(f.inv + 4 * min(v, f.fw - 1));
+        const float* sc = f.sline + __float_as_int(e.x) * 4;
+        const float we[3] = {e.y, e.z, e.w};
+        float t[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) t[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < f.nps) {
+            if (CPL == 4) {
+              const float4 q = *reinterpret_cast<const float4*>(sc + 4 * i);
+              t[0] = fmaf(we[i], q.x, t[0]);
+              t[1 % CPL] = fmaf(we[i], q.y, t[1 % CPL]);
+              t[2 % CPL] = fmaf(we[i], q.z, t[2 % CPL]);
+              t[3 % CPL] = fmaf(we[i], q.w, t[3 % CPL]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) t[k] = fmaf(we[i], sc[4 * i + k], t[k]);
+            }
+          }
+        }
+        if (v < f.fw) pr_red4<CPL>(f.grow + 64 * ps, f.hw4, t, act);
+      }
+    }
+    __syncwarp();  // scratch is rewritten by the next flush
   }
-  for (int s = 1; s < (1 << c.logl); s <<= 1) {
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], s);
-  }
+  f.grow += f.w4;
 }
 
-// Window of WIN footprint rows (rows cy .. cy+WIN-1) of dF per channel pass; WIN >= the tallest band.
+// Vertical pass: window of WIN footprint rows (rows cy .. cy+WIN-1) of U per channel pass; WIN >= the tallest band.
 template <int CPL, int WIN>
-__device__ __forceinline__ void pr_bwd_win(const PrBwdCol<CPL>& c, const float* yrec) {
+__device__ __forceinline__ void pr_bwd_win(PrBwdFlush& f, const float* gp /* tile + slot/bin */, const float* yrec,
+                                           int H, const bool (&act)[CPL]) {
+  using M = PrMap<14, CPL>;
   float acc[WIN][CPL];
 #pragma unroll
   for (int r = 0; r < WIN; ++r)
@@ -760,20 +869,20 @@ __device__ __forceinline__ void pr_bwd_win(const PrBwdCol<CPL>& c, const float* 
     for (int k = 0; k < CPL; ++k) acc[r][k] = 0.f;
   int cy = 0;
   bool open = false;
-  const float* grow = c.gq;
 #pragma unroll 1
-  for (int ph = 0; ph < 14; ++ph, grow += 14) {
+  for (int ph = 0; ph < 14; ++ph, gp += 14) {
     const int4 ca = *reinterpret_cast<const int4*>(yrec + ph * 8);
-    const float4 cb = *reinterpret_cast<const float4*>(yrec + ph * 8 + 4);
     if (ca.y <= 0) continue;
-    float t[CPL];
-    pr_bwd_hrow<CPL>(c, grow, t);
-    if (!open) {
-      cy = ca.x;
+    float g[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) g[k] = gp[M::koff(k) * 196];
+    if (!open) {  // first band: the row pointer starts at its first row (may be negative only in theory: bands
+      cy = ca.x;  // hold cells inside the map)
+      f.grow += (size_t)cy * f.w4;
       open = true;
     }
-    while (cy < ca.x) {  // row cy is complete (a gap of more than WIN rows just emits zero rows: never with
-      pr_bwd_red<CPL>(c, cy, acc[0]);  // adaptive sampling)
+    while (cy < ca.x) {  // row cy is complete (a gap wider than the window just emits zero rows: never happens with
+      pr_bwd_flush<CPL>(f, cy < H, acc[0], act);  // adaptive sampling)
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
 #pragma unroll
@@ -785,37 +894,19 @@ __device__ __forceinline__ void pr_bwd_win(const PrBwdCol<CPL>& c, const float* 
     float wy[WIN];
     wy[0] = __int_as_float(ca.z);
     wy[1] = __int_as_float(ca.w);
-    if (WIN > 2) wy[2] = cb.x;
-    if (WIN > 3) wy[WIN > 3 ? 3 : 0] = cb.y;
+    if (WIN > 2) {
+      const float4 cb = *reinterpret_cast<const float4*>(yrec + ph * 8 + 4);
+      wy[2 % WIN] = cb.x;
+      wy[3 % WIN] = cb.y;
+    }
 #pragma unroll
     for (int r = 0; r < WIN; ++r)
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) acc[r][k] = fmaf(wy[r], t[k], acc[r][k]);
+      for (int k = 0; k < CPL; ++k) acc[r][k] = fmaf(wy[r], g[k], acc[r][k]);
   }
   if (open) {
 #pragma unroll
-    for (int r = 0; r < WIN; ++r) pr_bwd_red<CPL>(c, cy + r, acc[r]);
-  }
-}
-
-// Bands taller than the window templates: every (output row, band row) pair is reduced on its own.
-template <int CPL>
-__device__ __forceinline__ void pr_bwd_gen(const PrBwdCol<CPL>& c, const float* yrec, const PrRecB* yrecB) {
-  const float* grow = c.gq;
-#pragma unroll 1
-  for (int ph = 0; ph < 14; ++ph, grow += 14) {
-    const float* yr = yrec + ph * 8;
-    const int ys = __float_as_int(yr[0]), ny = __float_as_int(yr[1]);
-    if (ny <= 0) continue;
-    float t[CPL];
-    pr_bwd_hrow<CPL>(c, grow, t);
-    for (int r = 0; r < ny; ++r) {
-      const float wy = r < 6 ? yr[2 + r] : __ldg(&yrecB[ph].w[r - 6]);
-      float u[CPL];
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) u[k] = wy * t[k];
-      pr_bwd_red<CPL>(c, ys + r, u);
-    }
+    for (int r = 0; r < WIN; ++r) pr_bwd_flush<CPL>(f, cy + r < H, acc[r], act);
   }
 }
 
@@ -830,29 +921,36 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
   extern __shared__ __align__(128) float smem[];
   float* wrec = smem;                                                      // [warps][2][232]: RoI blocks (A halves)
   float* tiles = wrec + kPrBwdWarps * 2 * kPrBlockFloats;                  // [warps][CH][196]: pooled-gradient tiles
-  float* tbls = tiles + kPrBwdWarps * M::STG;                              // [warps][kPrTblFloats]
-  int* tpas = reinterpret_cast<int*>(tbls + kPrBwdWarps * kPrTblFloats);   // [warps][kPrTblV]
-  float* scr = reinterpret_cast<float*>(tpas + kPrBwdWarps * kPrTblV);     // [warps][kPrScratch]
+  float* invs = tiles + kPrBwdWarps * M::STG;                              // [warps][2][kPrInvFloats]
+  float* scr = invs + kPrBwdWarps * 2 * kPrInvFloats;                      // [warps][kPrScratch]
   __shared__ int s_unit, s_next;
   __shared__ __align__(8) uint64_t bars[kPrBwdWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = lane >> 4;
   const int p = min(lane & 15, P - 1);  // idle lanes mirror the slot's last bin
   float* wbuf = wrec + warp * (2 * kPrBlockFloats);
+  float* ibuf = invs + warp * (2 * kPrInvFloats);
   float* tile = tiles + warp * M::STG;
-  float* mytbl = tbls + warp * kPrTblFloats;
-  int* mytpa = tpas + warp * kPrTblV;
   uint64_t* bar = &bars[warp];
   if (lane == 0) pr_mbar_init(bar);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
   uint32_t phase = 0;
   const int HW = H * W;
-  PrBwdCol<CPL> col;
-  col.HW = HW;
-  col.W = W;
-  col.H = H;
-  const int xi = lane & 15;
+  PrBwdFlush f;
+  f.sline = scr + warp * kPrScratch + slot * 64;
+  f.hw4 = (unsigned)HW * 4u;
+  f.w4 = (unsigned)W * 4u;
+  f.xi = lane & 15;
+  f.p = p;
+  auto issue_next = [&](int b, int idx, int begin) {  // RoI block + the head of its inverse table, no registers
+    pr_issue_block(wbuf + b * kPrBlockFloats, plan.blocksA + (size_t)(begin + idx) * kPrBlockSlots, lane);
+    const char* src = reinterpret_cast<const char*>(plan.inv + (size_t)(begin + idx) * kPrInvFloats) + lane * 16;
+    const uint32_t dst = pr_smem_u32(ibuf + b * kPrInvFloats) + lane * 16;
+#pragma unroll
+    for (int q = 0; q < kPrInvPrefetch / 512; ++q)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 512), "l"(src + q * 512) : "memory");
+  };
   const int nunits = plan.counter[1] * ngroups;
   for (;;) {
     __syncthreads();
@@ -867,13 +965,14 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
     const PrChunk ck = plan.chunks[j];
     const int cbase = cg * CH, nch = min(CH, C - cbase), nroi = ck.end - ck.begin;
     const uint32_t tile_bytes = (uint32_t)nch * PER * 4u;
-    float* gimg = gin + ((size_t)ck.img * C + cbase + D * slot) * HW;  // this slot's first channel plane
+    char* gimg = reinterpret_cast<char*>(gin + ((size_t)ck.img * C + cbase + D * slot) * HW);
+    bool act[CPL];
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) col.act[k] = (M::koff(k) + D * slot) < nch && !(dbg & 1);
+    for (int k = 0; k < CPL; ++k) act[k] = (M::koff(k) + D * slot) < nch && !(dbg & 1);
     int i = 0;
     if (lane == 0) i = atomicAdd(&s_next, 1);
     i = __shfl_sync(0xffffffffu, i, 0);
-    if (i < nroi) pr_issue_block(wbuf, plan.blocksA + (size_t)(ck.begin + i) * kPrBlockSlots, lane);
+    if (i < nroi) issue_next(0, i, ck.begin);
     pr_commit();
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -886,45 +985,36 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
       int inext = 0;
       if (lane == 0) inext = atomicAdd(&s_next, 1);
       inext = __shfl_sync(0xffffffffu, inext, 0);
-      if (inext < nroi)
-        pr_issue_block(wbuf + (buf ^ 1) * kPrBlockFloats, plan.blocksA + (size_t)(ck.begin + inext) * kPrBlockSlots,
-                       lane);
+      if (inext < nroi) issue_next(buf ^ 1, inext, ck.begin);
       pr_commit();
       const float* blk = wbuf + buf * kPrBlockFloats;
       const PrHdr hd = *reinterpret_cast<const PrHdr*>(blk);
       const float* yrec = blk + 15 * 8;
-      const PrRecB* blkB = plan.blocksB + (size_t)(ck.begin + i) * kPrBlockSlots;
+      float* inv = ibuf + buf * kPrInvFloats;
+      const int fmt = hd.pad & 0xff;
       const bool small = hd.nxmax <= 2 && hd.nymax <= 2;
-      // lanes per column (narrow footprints) and the table geometry
-      int logl = 0;
-      if (hd.fw <= 8) logl = hd.fw <= 2 ? 3 : hd.fw <= 4 ? 2 : 1;
-      const int nps = (hd.nimax + (1 << logl) - 1) >> logl;   // bins per lane
-      const int nv = hd.fw <= 16 ? 16 : hd.fw;                 // virtual columns
-      const bool band = hd.cls == PR_BAND && !((dbg & 2) && !small) && !((dbg & 4) && small) && hd.fw > 0 &&
-                        nv <= kPrTblV && nv * nps <= kPrTblFloats && nps <= P;
+      const bool band = hd.cls == PR_BAND && fmt != 0 && hd.nymax <= 4 && !((dbg & 2) && !small) &&
+                        !((dbg & 4) && small);
       if (band) {
-        // ---- inverse of the x bands: for every (column, lane part) the contiguous bins whose band covers it ------
-        const int shift_max = P - nps;  // windows of nps bins are shifted left to stay inside 0..13
-        for (int v = lane; v < nv; v += 32) {
-          float* wt = mytbl + v * nps;
-          for (int q = 0; q < nps; ++q) wt[q] = 0.f;
-          const int col = v >> logl, part = v & ((1 << logl) - 1);
-          const int x = hd.x0 + col;
-          int pa = -1, seen = 0;
-          if (col < hd.fw)
-            for (int pw = 0; pw < P; ++pw) {
-              const float* xr = blk + (1 + pw) * 8;
-              const int xs = __float_as_int(xr[0]), n = __float_as_int(xr[1]);
-              const int jx = x - xs;
-              if (jx >= 0 && jx < n) {
-                if (seen >= part * nps && seen < (part + 1) * nps) {
-                  if (pa < 0) pa = min(pw, shift_max);
-                  wt[pw - pa] = jx < 6 ? xr[2 + jx] : __ldg(&blkB[1 + pw].w[jx - 6]);
-                }
-                ++seen;
-              }
-            }
-          mytpa[v] = pa < 0 ? 0 : pa;
+        f.fmt = fmt;
+        f.logl = (hd.pad >> 8) & 0xff;
+        f.nps = (hd.pad >> 16) & 0xff;
+        f.fw = hd.fw;
+        f.inv = inv;
+        f.npass = (hd.fw + 15) >> 4;
+        if (fmt == 2 && hd.fw * 16 > kPrInvPrefetch) {  // very wide footprint: the tail of its table (exposed)
+          const float4* src = reinterpret_cast<const float4*>(plan.inv + (size_t)(ck.begin + i) * kPrInvFloats);
+          for (int q = kPrInvPrefetch / 16 + lane; q < hd.fw; q += 32) reinterpret_cast<float4*>(inv)[q] = __ldg(src + q);
+          __syncwarp();
+        }
+        const int col = fmt == 1 ? (f.xi >> f.logl) : f.xi;
+        f.grow = gimg + (size_t)(hd.x0 + col) * 4;
+        if (fmt == 1) {
+          const float* e = inv + f.xi * 8;
+          f.sc1 = f.sline + __float_as_int(e[0]) * 4;
+#pragma unroll
+          for (int q = 0; q < 7; ++q) f.w1[q] = e[1 + q];
+          f.red0 = (f.xi & ((1 << f.logl) - 1)) == 0 && col < hd.fw;
         }
       }
       pr_mbar_wait(bar, phase);  // this RoI's gradient tile has landed
@@ -932,20 +1022,11 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
       __syncwarp();
       const float* gp = tile + (D * slot) * PER + p;
       if (band) {
-        col.nps = nps;
-        col.logl = logl;
-        for (int v = xi; v < nv; v += 16) {  // 16 columns (or column parts) per pass, the same for both slots
-          const int cc = v >> logl;
-          col.gq = tile + (D * slot) * PER + mytpa[v];
-          col.wt = mytbl + v * nps;
-          col.gcol = gimg + hd.x0 + cc;
-          col.red = (v & ((1 << logl) - 1)) == 0 && cc < hd.fw;
-          if (hd.nymax <= 2) pr_bwd_win<CPL, 2>(col, yrec);
-          else if (hd.nymax <= 4) pr_bwd_win<CPL, 4>(col, yrec);
-          else pr_bwd_gen<CPL>(col, yrec, blkB + 15);
-        }
+        if (hd.nymax <= 2) pr_bwd_win<CPL, 2>(f, gp, yrec, H, act);
+        else pr_bwd_win<CPL, 4>(f, gp, yrec, H, act);
       } else if (hd.cls == PR_DIRECT || (hd.cls == PR_BAND && !(dbg & 6))) {
-        // ---- per-sample scatter in the reference's order (sparse / huge sampling grids): rare ------------------
+        // ---- per-sample scatter in the reference's order (no inverse table: sparse / huge sampling grids, bands
+        //      taller than four rows, more bins per column than the table formats hold): rare ---------------------
         const RoiGeom g = roi_geom(rois + (size_t)hd.roi * 5, scale, aligned, P, P, sampling_ratio, H, W);
         if ((lane & 15) < P) {
 #pragma unroll 1
@@ -961,8 +1042,8 @@ roi_align_bwd_pr_kernel(const float* __restrict__ gout, const float* __restrict_
                 if (tx.wl == 0.f && tx.wh == 0.f) continue;
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
-                  if (!col.act[k]) continue;
-                  float* b = gimg + (size_t)M::koff(k) * HW;
+                  if (!act[k]) continue;
+                  float* b = reinterpret_cast<float*>(gimg) + (size_t)M::koff(k) * HW;
                   pr_red_global(b + ty.lo * W + tx.lo, go[k] * ty.wl * tx.wl);
                   pr_red_global(b + ty.lo * W + tx.hi, go[k] * ty.wl * tx.wh);
                   pr_red_global(b + ty.hi * W + tx.lo, go[k] * ty.wh * tx.wl);
@@ -1058,6 +1139,7 @@ size_t roi_pr_workspace_bytes(int N, int R) {
   b += align_up((size_t)(3 * N * kPrNB + 1) * 4, 256);       // counts, starts, cursor
   b += align_up(((size_t)N + (size_t)R / 32 + 1) * sizeof(PrChunk), 256);
   b += 2 * align_up((size_t)R * kPrBlockBytes, 256);         // A and B halves
+  b += align_up((size_t)R * kPrInvBytes, 256);               // inverse x tables (backward)
   return b;
 }
 
@@ -1075,11 +1157,14 @@ static PrPlan pr_carve(void* ws, int N, int R) {
   p.blocksA = (PrRecA*)b;
   b += align_up((size_t)R * kPrBlockBytes, 256);
   p.blocksB = (PrRecB*)b;
+  b += align_up((size_t)R * kPrBlockBytes, 256);
+  p.inv = (float*)b;
   return p;
 }
 
-static int pr_build_plan(const PrPlan& plan, const float* rois, int N, int H, int W, int R, int P, float scale,
-                         int sampling_ratio, int aligned, int chunk, cudaStream_t stream) {
+static int pr_build_plan(PrPlan plan, const float* rois, int N, int H, int W, int R, int P, float scale,
+                         int sampling_ratio, int aligned, int chunk, cudaStream_t stream, bool want_inv = false) {
+  if (!want_inv) plan.inv = nullptr;
   CDDMSL_CUDA(cudaMemsetAsync(plan.counts, 0, (size_t)N * kPrNB * 4, stream));
   if (P == 14) {
     pr_plan_count_kernel<14><<<ceil_div(R, 256), 256, 0, stream>>>(rois, R, N, H, W, scale, sampling_ratio, aligned,
@@ -1153,7 +1238,7 @@ static int pr_fwd_launch(const float* in, const float* rois, float* out, const P
 static bool pr_geometry_bwd(int C, int H, int W, PrGeom* out) {
   (void)H;
   (void)W;
-  const long long per_warp = 2LL * kPrBlockBytes + (kPrTblFloats + kPrTblV + kPrScratch) * 4LL;
+  const long long per_warp = 2LL * kPrBlockBytes + 2LL * kPrInvBytes + kPrScratch * 4LL;
   for (int cpl : {4, 2, 1}) {
     if (g_roi_pr_cpl && cpl > g_roi_pr_cpl) continue;
     if (cpl > 1 && 2 * (cpl / 2) >= C) continue;
@@ -1197,7 +1282,7 @@ int roi_align_bwd_pr(const float* gout, const float* rois, float* gin, int N, in
   const int ngroups = ceil_div(C, g.CH);
   const int chunk = pr_chunk_size(R, ngroups);
   CDDMSL_CUDA(cudaMemsetAsync(gin, 0, (size_t)N * C * H * W * sizeof(float), stream));
-  int rc = pr_build_plan(plan, rois, N, H, W, R, P, scale, sampling_ratio, aligned, chunk, stream);
+  int rc = pr_build_plan(plan, rois, N, H, W, R, P, scale, sampling_ratio, aligned, chunk, stream, true);
   if (rc) return rc;
   const long long max_units = ((long long)N + R / chunk + 1) * ngroups;
   const int grid = (int)min((long long)sm_count(), max_units);
