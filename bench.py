@@ -256,23 +256,28 @@ def make_state(cfg, rank, world, dev, ops, dist, seed_offset=0):
     one = torch.ones(1, device=dev)
     last = {}
 
-    def align_fused(a, b, tag):
-        packed, norms = ops.align_pack(a, b)
+    def align_both():
+        """image-level (rcnn.py:305-317) and region-level (:455-468) losses of the step with ONE all-gather for both
+        packed buffers (the reference issues four; the collective is latency-bound at 4-64 KB per rank)."""
+        p1, n1 = ops.align_pack(a_it, a_is)
+        p2, n2 = ops.align_pack(a_rs, a_rt)
         if world > 1:
-            allp = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
-            dist.all_gather_into_tensor(allp, packed)
+            flat = torch.cat([p1.reshape(-1), p2.reshape(-1)])
+            allf = torch.empty((world, flat.numel()), dtype=flat.dtype, device=dev)
+            dist.all_gather_into_tensor(allf, flat)
+            all1 = allf[:, : p1.numel()].reshape((world,) + tuple(p1.shape))
+            all2 = allf[:, p1.numel():].reshape((world,) + tuple(p2.shape))
         else:
-            allp = packed.unsqueeze(0)
-        last[tag] = allp
-        return ops.align_loss(allp, norms, rank, one, True)
+            all1, all2 = p1.unsqueeze(0), p2.unsqueeze(0)
+        last["image"], last["region"] = all1, all2
+        return ops.align_loss(all1, n1, rank, one, True), ops.align_loss(all2, n2, rank, one, True)
 
     def events(steps):
         return [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
 
     def device_step(e=None):
         if e: e[4].record()
-        l_img = align_fused(a_it, a_is, "image")
-        l_reg = align_fused(a_rs, a_rt, "region")
+        l_img, l_reg = align_both()
         if e: e[5].record()
         if e: e[0].record()
         out = ops.roi_align(feat, rois, scale, P, P, cfg.sampling_ratio, True)
@@ -498,8 +503,7 @@ def run_ours(args):
 
     from cddmsl_b200 import _lib, ops
     from cddmsl_b200.layers import ROIAlign
-    from cddmsl_b200.modeling import (Box2BoxTransform, FastRCNNOutputLayers, caption_consistency_loss,
-                                      image_caption_consistency_loss)
+    from cddmsl_b200.modeling import Box2BoxTransform, FastRCNNOutputLayers, caption_consistency_losses
     from cddmsl_b200.structures import Boxes, Instances
 
     rank = int(os.environ.get("RANK", "0"))
@@ -633,8 +637,7 @@ def run_ours(args):
             inst.gt_classes = gg
             scores, deltas = head(xx)
             lc = head.losses((scores, deltas.detach()), [inst])["loss_cls"]
-            li = image_caption_consistency_loss(al[1], al[0])
-            lr = caption_consistency_loss(al[2], al[3])
+            li, lr = caption_consistency_losses(al[1], al[0], al[2], al[3])
             torch.autograd.backward([out, lc, li, lr], [out.detach(), one[0], one[0], one[0]])
             sc = torch.stack([lc.detach(), li.detach(), lr.detach(), lc.detach() * 0])
             ev_cmp[b].record(s_cmp)

@@ -68,6 +68,49 @@ def image_caption_consistency_loss(trgt: torch.Tensor, src: torch.Tensor,
     return caption_consistency_loss(trgt, src, group)
 
 
+class _CaptionConsistencyPair(torch.autograd.Function):
+    """Both branches of a training step (image level rcnn.py:305-317 and region level :455-468) with ONE all-gather:
+    the two packed, normalised buffers travel in one NCCL message (4 all-gathers in the reference, 2 with one call per
+    branch, 1 here -- the collective is latency-bound at 4-64 KB per rank)."""
+
+    @staticmethod
+    def forward(ctx, a1, b1, a2, b2, group):
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        p1, n1 = ops.align_pack(a1, b1)
+        p2, n2 = ops.align_pack(a2, b2)
+        if world > 1:
+            flat = torch.cat([p1.reshape(-1), p2.reshape(-1)])
+            allf = torch.empty((world, flat.numel()), dtype=flat.dtype, device=flat.device)
+            dist.all_gather_into_tensor(allf, flat, group=group)
+            all1 = allf[:, : p1.numel()].reshape((world,) + tuple(p1.shape))
+            all2 = allf[:, p1.numel():].reshape((world,) + tuple(p2.shape))
+        else:
+            all1, all2 = p1.unsqueeze(0), p2.unsqueeze(0)
+        want = any(ctx.needs_input_grad[:4])
+        l1, da1, db1 = ops.align_loss(all1, n1, rank, None, want)
+        l2, da2, db2 = ops.align_loss(all2, n2, rank, None, want)
+        if want:
+            ctx.save_for_backward(da1, db1, da2, db2)
+        ctx.have = want
+        return l1, l2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if not ctx.have:
+            raise RuntimeError("caption_consistency_losses: backward without a recorded forward")
+        da1, db1, da2, db2 = ctx.saved_tensors
+        return da1 * g1, db1 * g1, da2 * g2, db2 * g2, None
+
+
+def caption_consistency_losses(trgt_img: torch.Tensor, src_img: torch.Tensor, src_reg: torch.Tensor,
+                               tgt_reg: torch.Tensor, group: Optional["dist.ProcessGroup"] = None):
+    """(image-level loss, region-level loss) = (`image_caption_consistency_loss(trgt_img, src_img)`,
+    `caption_consistency_loss(src_reg, tgt_reg)`) with a single all-gather for both."""
+    assert trgt_img.shape == src_img.shape and src_reg.shape == tgt_reg.shape
+    return _CaptionConsistencyPair.apply(trgt_img, src_img, src_reg, tgt_reg, group)
+
+
 def kd_l1_loss(teacher: torch.Tensor, student: torch.Tensor) -> torch.Tensor:
     """KD regulariser of the image-level branch, rcnn.py:265-272: `L1Loss()(v2l(offline_backbone(src)).detach(),
     v2l(backbone(src)))` on the [B, 768] V2L features.  One kernel yields the loss and the student's gradient;

@@ -76,6 +76,25 @@ def test_reference_rcnn_lines_fixture(golden_dir):
     _close(kd_l1_loss(big.roll(1, 0), big).item(), ref, 1e-5, "kd loss, grid-stride")
 
 
+def test_pair_api_equals_two_single_calls():
+    """`caption_consistency_losses` (one all-gather for the image- and the region-level branch) == the two calls."""
+    from cddmsl_b200.modeling import (caption_consistency_loss, caption_consistency_losses,
+                                      image_caption_consistency_loss)
+
+    g = synth.generator(7)
+    ti, si = torch.randn(16, 256, generator=g), torch.randn(16, 256, generator=g)
+    sr, tr = torch.randn(256, 256, generator=g), torch.randn(256, 256, generator=g)
+    a = [t.to(DEV).requires_grad_(True) for t in (ti, si, sr, tr)]
+    b = [t.to(DEV).requires_grad_(True) for t in (ti, si, sr, tr)]
+    l1, l2 = caption_consistency_losses(*a)
+    (l1 * 0.5 + l2 * 2.0).backward()
+    m1, m2 = image_caption_consistency_loss(b[0], b[1]), caption_consistency_loss(b[2], b[3])
+    (m1 * 0.5 + m2 * 2.0).backward()
+    assert torch.equal(l1, m1) and torch.equal(l2, m2)
+    for x, y in zip(a, b):
+        assert torch.equal(x.grad, y.grad)
+
+
 def test_upstream_gradient_scale_is_applied():
     from cddmsl_b200.modeling import caption_consistency_loss, image_caption_consistency_loss
 
@@ -162,6 +181,13 @@ def _nccl_worker(rank, world, port, golden_dir, q):
             loss = fn(a, b)
             loss.backward()
             out[kind or "world2_"] = (loss.item(), a.grad.cpu().numpy(), b.grad.cpu().numpy())
+        # both branches through ONE all-gather (image level: operands (trgt, src); region level: (src, tgt))
+        from cddmsl_b200.modeling import caption_consistency_losses
+        w = np.load(os.path.join(golden_dir, "align_ref.npz"))
+        t = [torch.from_numpy(w[f"w2_{n}{rank}"]).to(dev).requires_grad_(True) for n in ("a", "b", "a", "b")]
+        l_img, l_reg = caption_consistency_losses(*t)
+        (l_img + l_reg).backward()
+        out["pair_"] = (l_img.item(), l_reg.item(), [x.grad.cpu().numpy() for x in t])
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -192,3 +218,8 @@ def test_two_ranks_over_nccl(golden_dir):
             _close(loss, w2[f"{kind}loss"], 1e-5, kind + "loss")
             _close(da, w2[f"{kind}da{r}"], 1e-4, kind + "da")
             _close(db, w2[f"{kind}db{r}"], 1e-4, kind + "db")
+        l_img, l_reg, grads = res[r]["pair_"]
+        _close(l_img, w2["w2_image_loss"], 1e-5, "pair image loss")
+        _close(l_reg, w2["w2_region_loss"], 1e-5, "pair region loss")
+        _close(grads[0], w2[f"w2_image_da{r}"], 1e-4, "pair image da")
+        _close(grads[3], w2[f"w2_region_db{r}"], 1e-4, "pair region db")
