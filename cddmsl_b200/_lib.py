@@ -47,6 +47,9 @@ SIGNATURES = {
     "cddmsl_align_pack_normalized": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "cddmsl_align_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "cddmsl_align_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cddmsl_contrastive_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cddmsl_softmax_target_loss_workspace_bytes": (_sz, [_i]),
+    "cddmsl_softmax_target_loss": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cddmsl_kd_l1_loss_workspace_bytes": (_sz, []),
     "cddmsl_kd_l1_loss": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -38,7 +38,8 @@ __device__ __forceinline__ const float* packed_row(const float* packed_all, int 
 // the inner product reads its four rows / four columns with one LDS.128 each.
 constexpr int kLT = 64, kLK = 16;
 __global__ void __launch_bounds__(256)
-align_logits_kernel(const float* __restrict__ packed_all, int n, int n_local, int D, float* __restrict__ S) {
+align_logits_kernel(const float* __restrict__ packed_all, int n, int n_local, int D, float logit_scale,
+                    float* __restrict__ S) {
   __shared__ __align__(16) float As[kLK][kLT + 4], Bs[kLK][kLT + 4];
   const int i0 = blockIdx.y * kLT, j0 = blockIdx.x * kLT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -101,11 +102,13 @@ align_logits_kernel(const float* __restrict__ packed_all, int n, int n_local, in
     const int i = i0 + ty * 4 + x, j = j0 + tx * 4;
     if (i >= n) continue;
     if ((n & 3) == 0 && j + 3 < n) {
-      *reinterpret_cast<float4*>(S + (size_t)i * n + j) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+      *reinterpret_cast<float4*>(S + (size_t)i * n + j) =
+          make_float4(acc[x][0] * logit_scale, acc[x][1] * logit_scale, acc[x][2] * logit_scale,
+                      acc[x][3] * logit_scale);
     } else {
 #pragma unroll
       for (int y = 0; y < 4; ++y)
-        if (j + y < n) S[(size_t)i * n + j + y] = acc[x][y];
+        if (j + y < n) S[(size_t)i * n + j + y] = acc[x][y] * logit_scale;
     }
   }
 }
@@ -194,7 +197,8 @@ constexpr int kGR = 8, kGJ = 1024, kGD = 64, kGP = 4;
 __global__ void __launch_bounds__(256)
 align_grad_kernel(const float* __restrict__ packed_all, const float* __restrict__ S,
                   const float* __restrict__ rowlse, const float* __restrict__ collse, int n, int n_local, int D,
-                  int row0, const float* __restrict__ grad_scale, float* __restrict__ da, float* __restrict__ db) {
+                  int row0, const float* __restrict__ grad_scale, float grad_mult, float* __restrict__ da,
+                  float* __restrict__ db) {
   __shared__ __align__(16) float coef[kGJ][kGR];
   __shared__ unsigned rowoff[kGJ];  // float offset of opposite row j inside packed_all (no division in the hot loop)
   const int gb = gridDim.x >> 1;
@@ -204,7 +208,7 @@ align_grad_kernel(const float* __restrict__ packed_all, const float* __restrict_
   if (!out) return;
   const int rows = min(kGR, n_local - l0);
   const int g0 = row0 + l0;
-  const float scale = (grad_scale ? *grad_scale : 1.f) * 0.5f / (float)n;
+  const float scale = (grad_scale ? *grad_scale : 1.f) * grad_mult * 0.5f / (float)n;
   const int tid = threadIdx.x, dl = tid & (kGD - 1), jp = tid / kGD;
   const int d = blockIdx.y * kGD + dl;
   const bool dok = d < D;
@@ -358,9 +362,22 @@ extern "C" size_t cddmsl_align_loss_workspace_bytes(int world, int n_local, int 
   return align_carve(nullptr, world * n_local).total;
 }
 
+extern "C" int cddmsl_contrastive_loss(const float* packed_all, const float* norms_local, int world, int n_local,
+                                       int D, int rank, float logit_scale, float grad_mult, const float* grad_scale,
+                                       float* loss, float* da, float* db, void* workspace, size_t workspace_bytes,
+                                       cddmsl_stream_t stream_);
+
 extern "C" int cddmsl_align_loss(const float* packed_all, const float* norms_local, int world, int n_local, int D,
                                  int rank, const float* grad_scale, float* loss, float* da, float* db,
                                  void* workspace, size_t workspace_bytes, cddmsl_stream_t stream_) {
+  return cddmsl_contrastive_loss(packed_all, norms_local, world, n_local, D, rank, 1.f, 1.f, grad_scale, loss, da, db,
+                                 workspace, workspace_bytes, stream_);
+}
+
+extern "C" int cddmsl_contrastive_loss(const float* packed_all, const float* norms_local, int world, int n_local,
+                                       int D, int rank, float logit_scale, float grad_mult, const float* grad_scale,
+                                       float* loss, float* da, float* db, void* workspace, size_t workspace_bytes,
+                                       cddmsl_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (world <= 0 || n_local < 0 || D <= 0 || rank < 0 || rank >= world || !loss) return CDDMSL_EINVAL;
   const int n = world * n_local;
@@ -376,14 +393,15 @@ extern "C" int cddmsl_align_loss(const float* packed_all, const float* norms_loc
   if (w.total > workspace_bytes) return CDDMSL_EWORKSPACE;
   const int tiles = ceil_div(n, kLT);
   const int row_blocks = ceil_div(n, kLseWarps);
-  align_logits_kernel<<<dim3(tiles, tiles), 256, 0, stream>>>(packed_all, n, n_local, D, w.S);
+  align_logits_kernel<<<dim3(tiles, tiles), 256, 0, stream>>>(packed_all, n, n_local, D, logit_scale, w.S);
   align_lse_kernel<<<row_blocks + ceil_div(n, 32), kLseWarps * 32, 0, stream>>>(w.S, n, row_blocks, w.rowlse,
                                                                                w.collse);
   align_loss_kernel<<<1, 256, 0, stream>>>(w.S, n, w.rowlse, w.collse, loss);
   count_launch(3);
   if ((da || db) && n_local > 0) {
     align_grad_kernel<<<dim3(2 * ceil_div(n_local, kGR), ceil_div(D, kGD)), 256, 0, stream>>>(
-        packed_all, w.S, w.rowlse, w.collse, n, n_local, D, rank * n_local, grad_scale, da, db);
+        packed_all, w.S, w.rowlse, w.collse, n, n_local, D, rank * n_local, grad_scale, grad_mult * logit_scale, da,
+        db);
     align_grad_finish_kernel<<<ceil_div(2 * n_local * 32, 256), 256, 0, stream>>>(packed_all, norms_local, n_local, D,
                                                                                   rank * n_local, da, db);
     count_launch(2);
@@ -460,5 +478,101 @@ extern "C" int cddmsl_kd_l1_loss(const float* teacher, const float* student, int
   kd_l1_kernel<<<(unsigned)blocks, kKdThreads, 0, stream>>>(teacher, student, (long long)numel, 1.0f / (float)numel,
                                                             grad_scale, loss, dstudent, partial, ticket);
   count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-softmax losses against a DENSE target matrix (RegionCLIP pretraining):
+//   mode 0  KL distillation   detectron2/modeling/meta_arch/clip_rcnn.py:597-600:
+//           F.kl_div(softmax(s).log(), t, 'batchmean') = sum_ik t_ik (log t_ik - log p_ik) / R   (0 log 0 = 0)
+//   mode 1  MIL cross-entropy detectron2/utils/comm.py:332-355 (avg_positives=False, weights=None):
+//           mean_i -log(sum_k t_ik p_ik)
+// logits [R, ld] (the first K columns count: the cosine-logit op appends a background column), target [R, K].
+// One warp per row: online max / sum-exp pass, then loss and d loss / d logits (columns >= K get 0).  The mean is a
+// fixed-order two-stage sum.
+// ------------------------------------------------------------------------------------------------
+namespace cddmsl {
+constexpr int kTgtWarps = 8;
+
+__global__ void __launch_bounds__(kTgtWarps * 32)
+softmax_target_rows_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ target, int R, int K,
+                           int mode, const float* __restrict__ grad_scale, float* __restrict__ row_loss,
+                           float* __restrict__ dlogits) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kTgtWarps + warp;
+  if (i >= R) return;
+  const float* s = logits + (size_t)i * ld;
+  const float* t = target + (size_t)i * K;
+  float m = -INFINITY;
+  for (int k = lane; k < K; k += 32) m = fmaxf(m, s[k]);
+  m = warp_max(m);
+  float z = 0.f, st = 0.f, stp = 0.f, stl = 0.f, sts = 0.f;  // sum exp, sum t, sum t*exp, sum t log t, sum t*s
+  for (int k = lane; k < K; k += 32) {
+    const float e = expf(s[k] - m), tk = t[k];
+    z += e;
+    st += tk;
+    stp += tk * e;
+    if (tk > 0.f) stl += tk * logf(tk);
+    sts += tk * (s[k] - m);
+  }
+  z = warp_sum(z);
+  st = warp_sum(st);
+  stp = warp_sum(stp);
+  stl = warp_sum(stl);
+  sts = warp_sum(sts);
+  const float logz = logf(z);
+  // KL: sum t (log t - (s - m - log z)) ;  MIL: -log(sum t p) = log z - log(sum t e)
+  const float loss = mode == 0 ? (stl - sts + st * logz) : (logz - logf(stp));
+  if (lane == 0) row_loss[i] = loss;
+  if (dlogits) {
+    const float gs = (grad_scale ? __ldg(grad_scale) : 1.f) / (float)R;
+    float* d = dlogits + (size_t)i * ld;
+    const float inv_z = 1.f / z, inv_stp = 1.f / stp;
+    for (int k = lane; k < ld; k += 32) {
+      float g = 0.f;
+      if (k < K) {
+        const float p = expf(s[k] - m) * inv_z;
+        g = mode == 0 ? (p * st - t[k]) : (p - t[k] * expf(s[k] - m) * inv_stp);
+      }
+      d[k] = g * gs;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += v[i];  // fixed order per thread, fixed tree below
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    *out = t / (float)n;
+  }
+}
+}  // namespace cddmsl
+
+extern "C" size_t cddmsl_softmax_target_loss_workspace_bytes(int R) { return ((size_t)(R > 0 ? R : 0) + 64) * 4; }
+
+extern "C" int cddmsl_softmax_target_loss(const float* logits, int ld, const float* target, int R, int K, int mode,
+                                          const float* grad_scale, float* loss, float* dlogits, void* workspace,
+                                          size_t workspace_bytes, cddmsl_stream_t stream_) {
+  using namespace cddmsl;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (R < 0 || K <= 0 || ld < K || !loss || (mode != 0 && mode != 1)) return CDDMSL_EINVAL;
+  if (R == 0) {  // mean over nothing
+    const float nanv = __builtin_nanf("");
+    CDDMSL_CUDA(cudaMemcpyAsync(loss, &nanv, sizeof(float), cudaMemcpyHostToDevice, stream));
+    return CDDMSL_OK;
+  }
+  if (!logits || !target || !workspace) return CDDMSL_EINVAL;
+  if (workspace_bytes < cddmsl_softmax_target_loss_workspace_bytes(R)) return CDDMSL_EWORKSPACE;
+  float* row_loss = (float*)workspace;
+  softmax_target_rows_kernel<<<ceil_div(R, kTgtWarps), kTgtWarps * 32, 0, stream>>>(logits, ld, target, R, K, mode,
+                                                                                   grad_scale, row_loss, dlogits);
+  mean_rows_kernel<<<1, 256, 0, stream>>>(row_loss, R, loss);
+  count_launch(2);
   return (int)cudaGetLastError();
 }

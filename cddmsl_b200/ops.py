@@ -580,3 +580,80 @@ def _kd_bwd(ctx, gloss, _gds):
 
 
 kd_l1.register_autograd(_kd_bwd, setup_context=_kd_setup)
+
+
+# ------------------------------------------------------------------------------ RegionCLIP pretraining losses
+@torch.library.custom_op("cddmsl_b200::contrastive_loss", mutates_args=(), device_types="cuda")
+def contrastive_loss(packed_all: Tensor, norms_local: Tensor, rank: int, logit_scale: float, grad_mult: float,
+                     want_grads: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """`align_loss` with a temperature (logits = logit_scale * A^ B^T) and a gradient multiplier (clip_rcnn.py:608-640
+    with comm.py:268-322).  Returns (loss[], da, db [n_local,D] or empty)."""
+    _lib.require_cuda(packed_all, "packed_all")
+    p = _f32c(packed_all)
+    world, two, n_local, d = p.shape
+    assert two == 2
+    dev = p.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    shape = (n_local, d) if want_grads else (0,)
+    da = torch.empty(shape, dtype=torch.float32, device=dev)
+    db = torch.empty(shape, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_align_loss_workspace_bytes(world, n_local, d), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.cddmsl_contrastive_loss(_lib.ptr(p), _lib.ptr(_f32c(norms_local)), world, n_local, d, rank,
+                                             float(logit_scale), float(grad_mult), None, _lib.ptr(loss),
+                                             _lib.ptr(da) if want_grads else None, _lib.ptr(db) if want_grads else None,
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "contrastive_loss")
+    return loss, da, db
+
+
+@contrastive_loss.register_fake
+def _(packed_all, norms_local, rank, logit_scale, grad_mult, want_grads):
+    world, _, n_local, d = packed_all.shape
+    shape = (n_local, d) if want_grads else (0,)
+    return packed_all.new_empty(()), packed_all.new_empty(shape), packed_all.new_empty(shape)
+
+
+TARGET_KL, TARGET_MIL = 0, 1
+
+
+@torch.library.custom_op("cddmsl_b200::softmax_target_loss", mutates_args=(), device_types="cuda")
+def softmax_target_loss(logits: Tensor, target: Tensor, mode: int, want_grad: bool) -> Tuple[Tensor, Tensor]:
+    """Row-softmax loss against a dense target (clip_rcnn.py:597-606): logits [R, ld >= K], target [R, K]; the first K
+    logit columns count.  Returns (loss[], d loss / d logits [R, ld] or empty)."""
+    _lib.require_cuda(logits, "logits")
+    lg, tg = _f32c(logits), _f32c(target)
+    r, ld = lg.shape
+    k = tg.shape[1]
+    assert tg.shape[0] == r and ld >= k
+    dev = lg.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dl = torch.empty_like(lg) if want_grad else torch.empty((0,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _ws(L.cddmsl_softmax_target_loss_workspace_bytes(r), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.cddmsl_softmax_target_loss(_lib.ptr(lg), ld, _lib.ptr(tg), r, k, int(mode), None, _lib.ptr(loss),
+                                                _lib.ptr(dl) if want_grad else None, _lib.ptr(ws), ws.numel(),
+                                                _lib.stream_ptr(dev)), "softmax_target_loss")
+    return loss, dl
+
+
+@softmax_target_loss.register_fake
+def _(logits, target, mode, want_grad):
+    return logits.new_empty(()), (torch.empty_like(logits) if want_grad else logits.new_empty((0,)))
+
+
+def _tgt_setup(ctx, inputs, output):
+    ctx.have = inputs[3]
+    if inputs[3]:
+        ctx.save_for_backward(output[1])
+
+
+def _tgt_bwd(ctx, gloss, _gdl):
+    if not ctx.have:
+        raise RuntimeError("softmax_target_loss: backward without a recorded gradient")
+    (dl,) = ctx.saved_tensors
+    return dl * gloss, None, None, None   # the target is the teacher's (detached) distribution / a label matrix
+
+
+softmax_target_loss.register_autograd(_tgt_bwd, setup_context=_tgt_setup)

@@ -173,6 +173,26 @@ int cddmsl_align_loss(const float* packed_all, const float* norms_local, int wor
                       const float* grad_scale, float* loss, float* da, float* db, void* workspace,
                       size_t workspace_bytes, cddmsl_stream_t stream);
 
+/* cddmsl_align_loss with a temperature and the gradient semantics of RegionCLIP's `gather_tensors`
+ * (detectron2/utils/comm.py:268-322, diffdist all_gather: every rank's identical loss back-propagates into every
+ * rank's rows, so the local rows receive `world` times the gradient GatherLayer keeps): the image-text matching loss
+ * of the pretraining model, detectron2/modeling/meta_arch/clip_rcnn.py:608-640 --
+ * logits = logit_scale * A^ B^T (logit_scale = 1 / matching_temp), loss = (CE(S, I) + CE(S^T, I)) / 2, gradients of
+ * the local rows multiplied by grad_mult.  (logit_scale = grad_mult = 1: cddmsl_align_loss.)  Same workspace. */
+int cddmsl_contrastive_loss(const float* packed_all, const float* norms_local, int world, int n_local, int D, int rank,
+                            float logit_scale, float grad_mult, const float* grad_scale, float* loss, float* da,
+                            float* db, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+
+/* Row-softmax losses against a dense target matrix, RegionCLIP pretraining (`region_concept_matching`,
+ * clip_rcnn.py:583-606): mode 0 = KL distillation `F.kl_div(softmax(s).log(), t, 'batchmean')` (:597-600),
+ * mode 1 = MILCrossEntropy(s, label_mtx) (detectron2/utils/comm.py:332-355, sum over positives, mean over rows).
+ * logits [R, ld] (first K columns count), target [R, K]; dlogits (nullable) [R, ld] = d loss / d logits * *grad_scale
+ * (device pointer, NULL = 1), zero in the columns >= K. */
+size_t cddmsl_softmax_target_loss_workspace_bytes(int R);
+int cddmsl_softmax_target_loss(const float* logits, int ld, const float* target, int R, int K, int mode,
+                               const float* grad_scale, float* loss, float* dlogits, void* workspace,
+                               size_t workspace_bytes, cddmsl_stream_t stream);
+
 /* KD regulariser of the image-level branch, detectron2/modeling/meta_arch/rcnn.py:265-272:
  * loss = L1Loss()(teacher.detach(), student) = mean |teacher - student| over `numel` elements ([B,768] V2L
  * features); dstudent (nullable, [numel]) = sign(student - teacher) * scale / numel with scale = *grad_scale

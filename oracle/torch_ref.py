@@ -266,3 +266,31 @@ def assign_classes(matched_idxs, matched_labels, gt_classes, num_classes: int):
         out[matched_labels == -1] = -1
         return out
     return torch.zeros_like(matched_idxs) + num_classes
+
+
+# ------------------------------------------------------------------ RegionCLIP pretraining losses (8f row 4)
+def mil_cross_entropy(x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """detectron2/utils/comm.py:339-355 with dim=-1, weights=None, avg_positives=False."""
+    logits = x - x.max(dim=1, keepdim=True).values.detach()
+    e = torch.exp(logits)
+    probs = e / e.sum(dim=-1, keepdim=True)
+    return (-torch.log(torch.sum(target * probs, dim=-1))).mean()
+
+
+def region_concept_losses(keep_region_feats, concept_emb, concept_scores, target_embs, label_mtx, matching_temp):
+    """detectron2/modeling/meta_arch/clip_rcnn.py:590-611 -> (loss_region_distill, loss_concept_contrastive)."""
+    f = keep_region_feats / keep_region_feats.norm(dim=-1, keepdim=True)
+    c = concept_emb / concept_emb.norm(dim=-1, keepdim=True)
+    distill = F.kl_div(F.softmax(f @ c.t() / matching_temp, dim=1).log(), concept_scores, reduction="batchmean")
+    t = target_embs / target_embs.norm(dim=-1, keepdim=True)
+    contrastive = mil_cross_entropy(f @ t.t() / matching_temp, label_mtx)
+    return distill, contrastive
+
+
+def image_text_matching_loss(region_feats_all, text_embs_all, matching_temp):
+    """clip_rcnn.py:624-640 on the gathered tensors."""
+    r = region_feats_all / region_feats_all.norm(dim=-1, keepdim=True)
+    t = text_embs_all / text_embs_all.norm(dim=-1, keepdim=True)
+    s = r @ t.t() / matching_temp
+    gt = torch.arange(s.shape[0])
+    return (F.cross_entropy(s, gt) + F.cross_entropy(s.t(), gt)) / 2.0

@@ -32,6 +32,9 @@ What it records (all seeded, fp32 / int64):
     tensors (single process with an identity gather, and under a real 2-process gloo group with the reference's
     `GatherLayer`).  THIS pins piece 4 to the reference itself.
 
+  * pretrain_ref.npz — RegionCLIP pretraining losses: the literal lines `clip_rcnn.py:590-611`, `:624-640` and the
+    literal class `MILCrossEntropy` (`utils/comm.py:332-355`) executed on seeded tensors.
+
 The tests never read /root/reference; they read these files.
 """
 import importlib.util
@@ -498,11 +501,70 @@ def align_ref_cases():
     print("align_ref: region/image single + world2, kd")
 
 
+def pretrain_ref_cases():
+    """pretrain_ref.npz: the literal lines detectron2/modeling/meta_arch/clip_rcnn.py:590-611 (region-concept KL
+    distillation + MIL contrastive loss) and :624-640 (image-text matching, single process) with the literal class
+    `MILCrossEntropy` of detectron2/utils/comm.py:332-355, executed on seeded tensors; gradients by autograd."""
+    import textwrap
+
+    import torch.nn.functional as F
+    from torch import nn
+
+    ns = {"torch": torch, "nn": nn, "F": F}
+    exec(_ref_lines("detectron2/utils/comm.py", 332, 355), ns)
+    body = _ref_lines("detectron2/modeling/meta_arch/clip_rcnn.py", 590, 611)
+    exec("def region_concept(self, keep_region_feats, concept_scores, target_embs, label_mtx, losses, "
+         "use_distill=True, use_contrastive=True):\n" + textwrap.indent(body, "    "), ns)
+    body = _ref_lines("detectron2/modeling/meta_arch/clip_rcnn.py", 624, 640)
+    exec("def image_text(self, global_feats, text_embs, losses):\n" + textwrap.indent(body, "    "), ns)
+    g = synth.generator(31)
+    out = {}
+    for tag, (r, d, k, temp) in {"small": (48, 64, 30, 0.01), "lvis": (40, 128, 1203, 0.01)}.items():
+        feats = torch.randn(r, d, generator=g)
+        concept_emb = torch.randn(k, d, generator=g)
+        teacher = torch.softmax(torch.randn(r, k, generator=g) * 3.0, dim=1)
+        teacher[0, :5] = 0.0                                     # exact zeros in the target (0 log 0 = 0)
+        tgt_idx = torch.randint(0, 12, (r,), generator=g)        # pseudo concept of every kept region
+        target_embs = concept_emb[tgt_idx]
+        label_mtx = (tgt_idx[:, None] == tgt_idx[None, :]).float()
+
+        class S:
+            pass
+
+        self_ = S()
+        self_.concept_emb, self_.matching_temp, self_.gather_gpus, self_.device = concept_emb, temp, False, torch.device("cpu")
+        x = feats.clone().requires_grad_(True)
+        losses = {}
+        ns["region_concept"](self_, x, teacher, target_embs, label_mtx, losses)
+        gd, = torch.autograd.grad(losses["loss_region_distill"], x, retain_graph=True)
+        gc, = torch.autograd.grad(losses["loss_concept_contrastive"], x)
+        out.update({f"feats_{tag}": feats.numpy(), f"concept_emb_{tag}": concept_emb.numpy(),
+                    f"teacher_{tag}": teacher.numpy(), f"target_embs_{tag}": target_embs.numpy(),
+                    f"label_mtx_{tag}": label_mtx.numpy(), f"temp_{tag}": np.array([temp]),
+                    f"distill_{tag}": losses["loss_region_distill"].detach().numpy(), f"distill_dx_{tag}": gd.numpy(),
+                    f"contrastive_{tag}": losses["loss_concept_contrastive"].detach().numpy(),
+                    f"contrastive_dx_{tag}": gc.numpy()})
+    n, d, temp = 24, 96, 0.07
+    a, b = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+
+    class S2:
+        matching_temp, gather_gpus, device = temp, False, torch.device("cpu")
+
+    aa, bb = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    losses = {}
+    ns["image_text"](S2(), aa, bb, losses)
+    losses["loss_img_txt_level"].backward()
+    out.update(it_feats=a.numpy(), it_text=b.numpy(), it_temp=np.array([temp]),
+               it_loss=losses["loss_img_txt_level"].detach().numpy(), it_dfeats=aa.grad.numpy(), it_dtext=bb.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, "pretrain_ref.npz"), **out)
+    print("pretrain_ref: region-concept small/lvis, image-text")
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
-    if len(sys.argv) > 1 and sys.argv[1] in ("box_reg", "match", "head_ref", "align_ref"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("box_reg", "match", "head_ref", "align_ref", "pretrain_ref"):
         {"box_reg": box_reg_cases, "match": match_cases, "head_ref": head_ref_cases,
-         "align_ref": align_ref_cases}[sys.argv[1]]()
+         "align_ref": align_ref_cases, "pretrain_ref": pretrain_ref_cases}[sys.argv[1]]()
         sys.exit(0)
     roi_cases()
     nms_cases()
@@ -512,5 +574,6 @@ if __name__ == "__main__":
     match_cases()
     head_ref_cases()
     align_ref_cases()
+    pretrain_ref_cases()
     sizes = {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")}
     print(sizes, sum(sizes.values()))

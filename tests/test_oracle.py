@@ -264,3 +264,25 @@ def test_matcher_oracle_and_host_mirror_match_reference_fixture(golden_dir):
                 m, l = fn(mqm)
                 assert np.array_equal(m.numpy(), f[f"matches_{tag}_{b}"]), (tag, b)
                 assert np.array_equal(l.numpy(), f[f"labels_{tag}_{b}"]), (tag, b)
+
+
+def test_oracle_pretraining_losses_equal_reference_clip_rcnn_lines(golden_dir):
+    """pretrain_ref.npz was produced by executing the literal lines clip_rcnn.py:590-611 / :624-640 with the literal
+    class MILCrossEntropy (utils/comm.py:332-355), read from the reference at generation time."""
+    p = np.load(os.path.join(golden_dir, "pretrain_ref.npz"))
+    for tag in ("small", "lvis"):
+        t = lambda k: torch.from_numpy(p[f"{k}_{tag}"])
+        for which, key in ((0, "distill"), (1, "contrastive")):
+            x = t("feats").clone().requires_grad_(True)
+            loss = torch_ref.region_concept_losses(x, t("concept_emb"), t("teacher"), t("target_embs"), t("label_mtx"),
+                                                   float(p[f"temp_{tag}"][0]))[which]
+            loss.backward()
+            assert np.allclose(loss.item(), p[f"{key}_{tag}"], rtol=1e-6), key
+            assert np.allclose(x.grad.numpy(), p[f"{key}_dx_{tag}"], rtol=1e-5, atol=1e-8), key
+    a = torch.from_numpy(p["it_feats"]).requires_grad_(True)
+    b = torch.from_numpy(p["it_text"]).requires_grad_(True)
+    loss = torch_ref.image_text_matching_loss(a, b, float(p["it_temp"][0]))
+    loss.backward()
+    assert np.allclose(loss.item(), p["it_loss"], rtol=1e-6)
+    assert np.allclose(a.grad.numpy(), p["it_dfeats"], rtol=1e-5, atol=1e-8)
+    assert np.allclose(b.grad.numpy(), p["it_dtext"], rtol=1e-5, atol=1e-8)
