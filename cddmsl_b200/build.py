@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcddmsl_b200.so")
-SOURCES = ["c_abi.cu", "roi_align.cu", "roi_align_cl.cu", "roi_align_pr.cu", "nms.cu", "clip_head.cu", "box_reg.cu", "match.cu", "align_loss.cu", "rpn_decode.cu"]
+SOURCES = ["c_abi.cu", "roi_align.cu", "roi_align_cl.cu", "roi_align_pr.cu", "roi_align_rw.cu", "nms.cu", "clip_head.cu", "box_reg.cu", "match.cu", "align_loss.cu", "rpn_decode.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

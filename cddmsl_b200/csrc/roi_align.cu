@@ -427,6 +427,12 @@ int roi_align_bwd_pr(const float* gout, const float* rois, float* gin, int N, in
                      float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
 bool roi_pr_bwd_eligible(int N, int C, int H, int W, int R, int P);
 int tune_roi_pr(const char* key, int value);
+// row-walk backward (roi_align_rw.cu): one warp per (RoI, 32 channels), one RED per footprint cell and channel
+bool roi_rw_eligible(int N, int C, int H, int W, int R, int P);
+size_t roi_rw_workspace_bytes(int N, int C, int H, int W, int R);
+int roi_align_bwd_rw(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
+                     float scale, int sampling_ratio, int aligned, void* ws, cudaStream_t stream);
+int tune_roi_rw(const char* key, int value);
 int roi_align_bwd_cl(const float* gout, const float* rois, float* gin, int N, int C, int H, int W, int R, int P,
                      float scale, int sampling_ratio, int aligned, float* gt, cudaStream_t stream);
 
@@ -440,14 +446,15 @@ int tune_roi(const char* key, int value) {
   else if (!strcmp(key, "roi_bwd_cpl")) g_bwd_cpl = value;
   else if (!strcmp(key, "roi_gpc")) g_roi_gpc = value;
   else if (!strcmp(key, "roi_tma")) g_roi_tma = value;
-  else return tune_roi_pr(key, value);
+  else return tune_roi_pr(key, value) || tune_roi_rw(key, value);
   return 1;
 }
 
 static size_t roi_workspace_bytes(int N, int C, int H, int W, int R) {
   N = N > 0 ? N : 0, C = C > 0 ? C : 0, H = H > 0 ? H : 0, W = W > 0 ? W : 0, R = R > 0 ? R : 0;
   const size_t a = roi_cl_workspace_bytes(N, C, H, W), b = roi_pr_workspace_bytes(N, R);
-  return (a > b ? a : b) + 256;
+  const size_t c = roi_rw_workspace_bytes(N, C, H, W, R);
+  return (a > b ? (a > c ? a : c) : (b > c ? b : c)) + 256;
 }
 
 }  // namespace cddmsl
@@ -523,6 +530,12 @@ extern "C" int cddmsl_roi_align_bwd(const float* gout, const float* rois, float*
       workspace_bytes >= roi_pr_workspace_bytes(N, R) && roi_pr_bwd_eligible(N, C, H, W, R, PH))
     return roi_align_bwd_pr(gout, rois, gin, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned, workspace,
                             stream);
+  if (PH == PW && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+      workspace_bytes >= roi_rw_workspace_bytes(N, C, H, W, R) && roi_rw_eligible(N, C, H, W, R, PH)) {
+    const int rc = roi_align_bwd_rw(gout, rois, gin, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned,
+                                    workspace, stream);
+    if (rc != -1000) return rc;  // -1000: no tensor map available, nothing was launched
+  }
   if (g_use_cl && roi_cl_eligible(N, C, H, W, PH, PW) && workspace &&
       workspace_bytes >= roi_cl_workspace_bytes(N, C, H, W) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
     return roi_align_bwd_cl(gout, rois, gin, N, C, H, W, R, PH, spatial_scale, sampling_ratio, aligned,

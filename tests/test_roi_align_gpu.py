@@ -125,6 +125,39 @@ def test_every_kernel_family_on_the_14x14_shape(knobs):
     _close(gin, c_ref.roi_align_bwd(gout, rois, feat.shape, 1.0 / 16, 0, True), BWD_RTOL)
 
 
+@pytest.mark.parametrize("channels,sr,aligned", [(64, 0, True), (96, 0, False), (32, 2, True), (160, 1, True)])
+def test_row_walk_backward(channels, sr, aligned):
+    """roi_align_rw.cu (default backward for 14x14, C % 32 == 0): random boxes of every size, boxes hanging over all
+    four borders, degenerate and whole-map boxes, a box on an out-of-range image index, RoIs with > 10 samples per bin
+    (reference-shaped slow path) and fixed sampling grids that are not monotone (slow path); against the oracle and
+    against the round-1 channels-last kernel."""
+    from cddmsl_b200 import _lib
+
+    g = synth.generator(58 + channels)
+    shape = (2, channels, 38, 63)
+    rois = synth.make_rois(synth.PathConfig("t", 2, 600, 1000, 48, 5), g).numpy()
+    extra = np.array([[0, -200, -100, 1300, 700], [1, 0, 0, 1008, 608], [0, 990, 590, 1100, 700], [1, -50, 300, 30, 330],
+                      [0, 500, -40, 530, 20], [1, 100, 100, 100, 100], [0, 3, 3, 5, 600], [1, 2, 2, 1000, 9],
+                      [0, 0, 0, 16, 16], [1, 1007, 607, 1008, 608], [5, 10, 10, 200, 200],
+                      [0, -3000, -3000, 4000, 4000]], dtype=np.float32)
+    rois = np.concatenate([rois, extra]).astype(np.float32)
+    gout = torch.randn(rois.shape[0], channels, 14, 14, generator=g).numpy()
+    # an image index outside the batch is undefined behaviour in the reference (and in the oracle): the kernels skip
+    # such a RoI, so the oracle sees the list without it
+    valid = rois[:, 0] < shape[0]
+    want = c_ref.roi_align_bwd(gout[valid], rois[valid], shape, 1.0 / 16, sr, aligned)
+    feat = np.zeros(shape, np.float32)
+    _, gin = _run(feat, rois, (14, 14), 1.0 / 16, sr, aligned, gout=gout)
+    _close(gin, want, BWD_RTOL)
+    assert _lib.tune("roi_rw", 0)
+    try:
+        _, gin_cl = _run(feat, rois, (14, 14), 1.0 / 16, sr, aligned, gout=gout)
+    finally:
+        _lib.tune("roi_rw", 1)
+    _close(gin_cl, want, BWD_RTOL)
+    assert not np.array_equal(gin, gin_cl)   # two different kernels ran
+
+
 def test_wide_bands_and_sparse_sampling_grids():
     """Plane-resident classes beyond the common ones: RoIs wider than 6 cells per bin (B halves of the records), a
     fixed sampling grid on huge bins (per-sample path), boxes hanging over every border, on a map with H*W odd."""
