@@ -125,7 +125,8 @@ def test_every_kernel_family_on_the_14x14_shape(knobs):
     _close(gin, c_ref.roi_align_bwd(gout, rois, feat.shape, 1.0 / 16, 0, True), BWD_RTOL)
 
 
-@pytest.mark.parametrize("channels,sr,aligned", [(64, 0, True), (96, 0, False), (32, 2, True), (160, 1, True)])
+@pytest.mark.parametrize("channels,sr,aligned", [(64, 0, True), (96, 0, False), (32, 2, True), (160, 1, True),
+                                                 (64, 2, False), (64, 3, True)])
 def test_row_walk_backward(channels, sr, aligned):
     """roi_align_rw.cu (default backward for 14x14, C % 32 == 0): random boxes of every size, boxes hanging over all
     four borders, degenerate and whole-map boxes, a box on an out-of-range image index, RoIs with > 10 samples per bin
@@ -147,13 +148,21 @@ def test_row_walk_backward(channels, sr, aligned):
     valid = rois[:, 0] < shape[0]
     want = c_ref.roi_align_bwd(gout[valid], rois[valid], shape, 1.0 / 16, sr, aligned)
     feat = np.zeros(shape, np.float32)
-    _, gin = _run(feat, rois, (14, 14), 1.0 / 16, sr, aligned, gout=gout)
-    _close(gin, want, BWD_RTOL)
-    assert _lib.tune("roi_rw", 0)
+    assert _lib.tune("roi_rw_min_units", 0)   # small lists normally stay on the channels-last kernel
     try:
+        _, gin = _run(feat, rois, (14, 14), 1.0 / 16, sr, aligned, gout=gout)
+        _close(gin, want, BWD_RTOL)
+        if channels % 64 == 0:
+            assert _lib.tune("roi_rw_cpl", 2)     # two channels per lane (knob)
+            _, gin2 = _run(feat, rois, (14, 14), 1.0 / 16, sr, aligned, gout=gout)
+            _lib.tune("roi_rw_cpl", 1)
+            _close(gin2, want, BWD_RTOL)
+        assert _lib.tune("roi_rw", 0)
         _, gin_cl = _run(feat, rois, (14, 14), 1.0 / 16, sr, aligned, gout=gout)
     finally:
         _lib.tune("roi_rw", 1)
+        _lib.tune("roi_rw_cpl", 1)
+        _lib.tune("roi_rw_min_units", 65536)
     _close(gin_cl, want, BWD_RTOL)
     assert not np.array_equal(gin, gin_cl)   # two different kernels ran
 
