@@ -581,7 +581,8 @@ roi_align_bwd_rw_kernel(const __grid_constant__ CUtensorMap gmap, const float* _
 }
 
 int g_roi_rw = 1;      // tuning knob "roi_rw": 1 = use this backward where eligible
-int g_roi_rw_k = 4;    // channel groups per visit of a RoI ("roi_rw_k")
+int g_roi_rw_k = 2;    // channel groups per visit of a RoI ("roi_rw_k"; VOC shape: 1 -> 1.98, 2 -> 1.97, 4 -> 2.09, 8 -> 2.68 ms;
+                       // an L2 evict_last hint on the REDs changes nothing, evict_first on the tile loads costs 0.1 ms)
 int g_roi_rw_min_units = 65536;  // below this many (RoI, 32-channel) units the channels-last kernel is faster: the
                                  // persistent grid does not fill and the plan kernel's latency shows
                                  // ("roi_rw_min_units"; 1024 RoIs x 1024 channels: 0.45 ms there, 0.77 ms here)
