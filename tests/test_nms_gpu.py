@@ -104,6 +104,17 @@ def test_above_40000_boxes_branch():
     assert np.array_equal(got, c_ref.batched_nms(boxes.numpy(), scores.numpy(), idxs.numpy(), 0.7, coord_trick=False))
 
 
+@pytest.mark.parametrize("m,k,thr", [(24576, 1, 0.7), (30001, 6, 0.5), (65536, 3, 0.7)])
+def test_large_single_image_bit_exact(m, k, thr):
+    """24 576 - 65 536 boxes in one image: same keep list as the oracle, incl. score ties, a ragged last 64-box block
+    and per-class suppression (the scan's removed-bitmap spans more than one pass of 256 column words here)."""
+    g = synth.generator(77 + m)
+    boxes, scores, idxs = synth.make_nms_inputs(m, 1024, 2048, g, num_classes=k, tie_frac=0.01)
+    got = _gpu(boxes, scores, idxs, thr)
+    want = c_ref.batched_nms(boxes.numpy(), scores.numpy(), idxs.numpy(), thr, coord_trick=False)
+    assert np.array_equal(got, _canon(want, scores.numpy()))
+
+
 def test_large_properties_256k():
     """configs[4] upper end (256k boxes): sorted by score, idempotent, and no kept pair overlaps above thr
     (checked on the top-scoring 4096 kept boxes with the exact fp32 formula)."""
