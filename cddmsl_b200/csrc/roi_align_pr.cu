@@ -465,6 +465,38 @@ __device__ __forceinline__ float pr_hblend(const float* a /* shared */, const fl
   return h;
 }
 
+// The same blend for two channel slots at once with packed fp32x2 arithmetic (FMUL2 / FFMA2): per element the very
+// operations of pr_hblend, so the results are bit-identical; the weight pairs (w, w) are built once per RoI.
+template <int NXT>
+__device__ __forceinline__ float2 pr_hblend2(const float* a0 /* shared */, const float* a1, const float2 (&wx2)[NXT]) {
+  float2 h = __fmul2_rn(wx2[0], make_float2(a0[0], a1[0]));
+#pragma unroll
+  for (int j = 1; j < NXT; ++j) h = __ffma2_rn(wx2[j], make_float2(a0[j], a1[j]), h);
+  return h;
+}
+// all CPL slots of one map row
+template <int P, int CPL, int NXT>
+__device__ __forceinline__ void pr_hblend_all(float (&h)[CPL], const float* ra, int PS, const float (&wx)[NXT],
+                                              const float2 (&wx2)[NXT]) {
+  using M = PrMap<P, CPL>;
+  if constexpr (CPL % 2 == 0 && NXT <= 6) {
+#pragma unroll
+    for (int k = 0; k < CPL; k += 2) {
+      const float2 v = pr_hblend2<NXT>(ra + M::koff(k) * PS, ra + M::koff(k + 1) * PS, wx2);
+      h[k] = v.x;
+      h[k + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) h[k] = pr_hblend<NXT>(ra + M::koff(k) * PS, wx);
+  }
+}
+template <int NXT>
+__device__ __forceinline__ void pr_pair_wx(float2 (&wx2)[NXT], const float (&wx)[NXT]) {
+#pragma unroll
+  for (int j = 0; j < NXT; ++j) wx2[j] = make_float2(wx[j], wx[j]);
+}
+
 // x weights of this lane's bin: the first six from the prefetched record, wider bands from the B half in global memory
 template <int NXT>
 __device__ __forceinline__ void pr_load_wx(float (&wx)[NXT], const float* xrec /* shared */, const PrRecB* xrecB) {
@@ -482,6 +514,8 @@ __device__ __forceinline__ void pr_fwd_win2(const float* a0, const float (&wx)[N
   float hA[CPL], hB[CPL];
 #pragma unroll
   for (int k = 0; k < CPL; ++k) hA[k] = hB[k] = 0.f;
+  float2 wx2[NXT];
+  pr_pair_wx<NXT>(wx2, wx);
   int cy = -0x40000000;
   bool flip = false;  // false: A = row cy, B = row cy + 1
   int4 yn = *reinterpret_cast<const int4*>(yrec);  // warp-uniform; the next record is fetched a row ahead
@@ -493,20 +527,12 @@ __device__ __forceinline__ void pr_fwd_win2(const float* a0, const float (&wx)[N
     if (yr.y > 0 && ys != cy) {
       const float* ra = a0 + (ys + 1) * RS;
       if (ys == cy + 1) {  // slide: the new bottom row replaces the old top row
-        if (!flip) {
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) hA[k] = pr_hblend<NXT>(ra + M::koff(k) * PS, wx);
-        } else {
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) hB[k] = pr_hblend<NXT>(ra + M::koff(k) * PS, wx);
-        }
+        if (!flip) pr_hblend_all<P, CPL, NXT>(hA, ra, PS, wx, wx2);
+        else pr_hblend_all<P, CPL, NXT>(hB, ra, PS, wx, wx2);
         flip = !flip;
       } else {
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          hA[k] = pr_hblend<NXT>(ra - RS + M::koff(k) * PS, wx);
-          hB[k] = pr_hblend<NXT>(ra + M::koff(k) * PS, wx);
-        }
+        pr_hblend_all<P, CPL, NXT>(hA, ra - RS, PS, wx, wx2);
+        pr_hblend_all<P, CPL, NXT>(hB, ra, PS, wx, wx2);
         flip = false;
       }
       cy = ys;
@@ -527,6 +553,8 @@ __device__ __forceinline__ void pr_fwd_win(const float* a0, const float (&wx)[NX
   for (int r = 0; r < WIN; ++r)
 #pragma unroll
     for (int k = 0; k < CPL; ++k) hw[r][k] = 0.f;
+  float2 wx2[NXT];
+  pr_pair_wx<NXT>(wx2, wx);
   int cy = -0x40000000;
   int4 na = *reinterpret_cast<const int4*>(yrec);
   float4 nb = *reinterpret_cast<const float4*>(yrec + 4);
@@ -546,11 +574,10 @@ __device__ __forceinline__ void pr_fwd_win(const float* a0, const float (&wx)[NX
       for (int s = 0; s < d; ++s) {
         const float* ra = a0 + min(cy + WIN + s, H) * RS;
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
+        for (int k = 0; k < CPL; ++k)
 #pragma unroll
           for (int r = 0; r + 1 < WIN; ++r) hw[r][k] = hw[r + 1][k];
-          hw[WIN - 1][k] = pr_hblend<NXT>(ra + M::koff(k) * PS, wx);
-        }
+        pr_hblend_all<P, CPL, NXT>(hw[WIN - 1], ra, PS, wx, wx2);
       }
       cy = ys;
     }
