@@ -539,7 +539,20 @@ __device__ __forceinline__ void pr_fwd_win2(const float* a0, const float (&wx)[N
     }
     const float w0 = __int_as_float(yr.z), w1 = __int_as_float(yr.w);
     const float wa = flip ? w1 : w0, wb = flip ? w0 : w1;
-    sk.row([&](int k) { return fmaf(wb, hB[k], wa * hA[k]); });
+    if constexpr (CPL % 2 == 0) {  // vertical blend of two channel slots per instruction (same operations per element)
+      float o[CPL];
+      const float2 wa2 = make_float2(wa, wa), wb2 = make_float2(wb, wb);
+#pragma unroll
+      for (int k = 0; k < CPL; k += 2) {
+        const float2 t = __ffma2_rn(wb2, make_float2(hB[k], hB[k + 1]),
+                                    __fmul2_rn(wa2, make_float2(hA[k], hA[k + 1])));
+        o[k] = t.x;
+        o[k + 1] = t.y;
+      }
+      sk.row([&](int k) { return o[k]; });
+    } else {
+      sk.row([&](int k) { return fmaf(wb, hB[k], wa * hA[k]); });
+    }
   }
 }
 
@@ -588,12 +601,26 @@ __device__ __forceinline__ void pr_fwd_win(const float* a0, const float (&wx)[NX
     if (WIN > 3) wy[WIN > 3 ? 3 : 0] = cb.y;
     if (WIN > 4) wy[WIN > 4 ? 4 : 0] = cb.z;
     if (WIN > 5) wy[WIN > 5 ? 5 : 0] = cb.w;
-    sk.row([&](int k) {
-      float o = wy[0] * hw[0][k];
+    if constexpr (CPL % 2 == 0) {
+      float o[CPL];
 #pragma unroll
-      for (int r = 1; r < WIN; ++r) o = fmaf(wy[r], hw[r][k], o);
-      return o;
-    });
+      for (int k = 0; k < CPL; k += 2) {
+        float2 t = __fmul2_rn(make_float2(wy[0], wy[0]), make_float2(hw[0][k], hw[0][k + 1]));
+#pragma unroll
+        for (int r = 1; r < WIN; ++r)
+          t = __ffma2_rn(make_float2(wy[r], wy[r]), make_float2(hw[r][k], hw[r][k + 1]), t);
+        o[k] = t.x;
+        o[k + 1] = t.y;
+      }
+      sk.row([&](int k) { return o[k]; });
+    } else {
+      sk.row([&](int k) {
+        float o = wy[0] * hw[0][k];
+#pragma unroll
+        for (int r = 1; r < WIN; ++r) o = fmaf(wy[r], hw[r][k], o);
+        return o;
+      });
+    }
   }
 }
 
