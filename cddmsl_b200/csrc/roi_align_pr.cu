@@ -628,7 +628,8 @@ __device__ __forceinline__ void pr_fwd_win(const float* a0, const float (&wx)[NX
 template <int P, int CPL, int NXT, class Sink>
 __device__ __forceinline__ void pr_fwd_gen(const float* a0, const float (&wx)[NXT], const float* yrec,
                                            const PrRecB* yrecB, int RS, int PS, Sink& sk) {
-  using M = PrMap<P, CPL>;
+  float2 wx2[NXT];
+  pr_pair_wx<NXT>(wx2, wx);
 #pragma unroll 1
   for (int ph = 0; ph < P; ++ph) {
     const float* yr = yrec + ph * 8;
@@ -640,8 +641,10 @@ __device__ __forceinline__ void pr_fwd_gen(const float* a0, const float (&wx)[NX
 #pragma unroll 1
     for (int r = 0; r < ny; ++r, ra += RS) {
       const float wy = r < 6 ? yr[2 + r] : __ldg(&yrecB[ph].w[r - 6]);
+      float h[CPL];
+      pr_hblend_all<P, CPL, NXT>(h, ra, PS, wx, wx2);
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) acc[k] = fmaf(wy, pr_hblend<NXT>(ra + M::koff(k) * PS, wx), acc[k]);
+      for (int k = 0; k < CPL; ++k) acc[k] = fmaf(wy, h[k], acc[k]);
     }
     sk.row([&](int k) { return acc[k]; });
   }
