@@ -32,12 +32,18 @@
 
 namespace cddmsl {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;  // BK * 4 B = 128 B = one swizzle row
-constexpr int TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;     // 16 KB
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;    // A hi, A lo, B hi, B lo
-constexpr int TC_THREADS = 448;  // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 10-13 epilogue
-constexpr uint32_t TC_TMEM_COLS = 256;  // two 128-column fp32 accumulators
+// 128 x 256 output tiles: with fp32 operands the 128 x 128 version moved 5.4 GB from L2 per GEMM (5.2 TB/s, the L2
+// limit; ncu round 2: tensor pipe 50 %); a 256-wide B tile cuts that to 4.0 GB and the shared-memory reads per flop
+// of the three MMAs by a quarter.
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32;  // BK * 4 B = 128 B = one swizzle row
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;        // 32 KB
+constexpr int TC_OFF_ALO = TC_A_BYTES, TC_OFF_BHI = 2 * TC_A_BYTES, TC_OFF_BLO = 2 * TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A hi, A lo, B hi, B lo = 96 KB
+constexpr int TC_SPLIT_WARPS = (TC_BM + TC_BN) / 32;              // one thread per operand row
+constexpr int TC_THREADS = (2 + TC_SPLIT_WARPS + 4) * 32;  // warp 0 TMA, warp 1 MMA, 12 split warps, 4 epilogue warps
+constexpr uint32_t TC_TMEM_COLS = 2 * TC_BN;  // two fp32 accumulators of TC_BN columns (all 512 columns of the SM)
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,7 +155,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 8);   // one arrival per split warp
+      mbar_init(&conv_bar[s], TC_SPLIT_WARPS);   // one arrival per split warp
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -180,9 +186,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint32_t ph = (g / TC_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);  // first pass over the ring falls through (barrier parity starts at 0)
           uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], 2 * TC_TILE_BYTES);
-          tma_load_2d(st, &map_a, kb * TC_BK, m0, &full_bar[s]);                      // A hi slot
-          tma_load_2d(st + 2 * TC_TILE_BYTES, &map_b, kb * TC_BK, n0, &full_bar[s]);  // B hi slot
+          mbar_expect_tx(&full_bar[s], TC_A_BYTES + TC_B_BYTES);
+          tma_load_2d(st, &map_a, kb * TC_BK, m0, &full_bar[s]);               // A hi slot
+          tma_load_2d(st + TC_OFF_BHI, &map_b, kb * TC_BK, n0, &full_bar[s]);  // B hi slot
         }
       }
     }
@@ -203,8 +209,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
-        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_TILE_BYTES);
-        const uint64_t b_hi = make_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = make_desc_sw128(st + 3 * TC_TILE_BYTES);
+        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_OFF_ALO);
+        const uint64_t b_hi = make_desc_sw128(st + TC_OFF_BHI), b_lo = make_desc_sw128(st + TC_OFF_BLO);
         if (lane == 0) {
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
@@ -228,12 +234,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         __syncwarp();
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + TC_SPLIT_WARPS) {
     // ===================== split (hi / lo) warps =====================
-    // 256 threads: thread u < 128 rewrites row u of the A tile, thread u >= 128 row u-128 of the B tile
+    // 384 threads: thread u < 128 rewrites row u of the A tile, thread u >= 128 row u-128 of the B tile
     const int u = threadIdx.x - 64;
-    const int t = u & 127;
-    const int op = u >> 7;
+    const int op = u >= TC_BM ? 1 : 0;
+    const int t = op ? u - TC_BM : u;
     int g = 0, it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       float ss = 0.f;
@@ -242,8 +248,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t ph = (g / TC_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
-        float4* hi = reinterpret_cast<float4*>(st + (size_t)op * 2 * TC_TILE_BYTES) + t * 8;
-        float4* lo = reinterpret_cast<float4*>(st + (size_t)(op * 2 + 1) * TC_TILE_BYTES) + t * 8;
+        float4* hi = reinterpret_cast<float4*>(st + (op ? TC_OFF_BHI : 0)) + t * 8;
+        float4* lo = reinterpret_cast<float4*>(st + (op ? TC_OFF_BLO : TC_OFF_ALO)) + t * 8;
         float4 v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = hi[c ^ (t & 7)];  // swizzled visiting order: conflict-free per quarter warp
@@ -269,7 +275,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue warps (10-13): a warp may touch TMEM lanes [32 * (warp % 4), +32)
+    // ===================== epilogue warps (the last four): a warp may touch TMEM lanes [32 * (warp % 4), +32)
     const int lg = warp & 3;
     const int row_in_tile = lg * 32 + lane;
     int it = 0;
@@ -465,10 +471,10 @@ __global__ void clip_head_tc_transpose_w_kernel(const float* __restrict__ wall, 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// row-major fp32 [rows, cols] (ld floats between rows), box [TC_BK cols x 128 rows], 128-byte swizzle
-static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld) {
+// row-major fp32 [rows, cols] (ld floats between rows), box [TC_BK cols x box_rows rows], 128-byte swizzle
+static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_rows) {
   return tma_encode_2d_f32(m, base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld * 4,
-                           TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)
+                           TC_BK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)
              ? CDDMSL_EINVAL
              : 0;
 }
@@ -476,9 +482,9 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int l
 static int launch_gemm(const float* A, int M, int lda, const float* B, int N, int ldb, int K, TcEpilogue ep,
                        cudaStream_t stream) {
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, A, M, K, lda);
+  int rc = make_map(&ma, A, M, K, lda, TC_BM);
   if (rc) return rc;
-  rc = make_map(&mb, B, N, K, ldb);
+  rc = make_map(&mb, B, N, K, ldb, TC_BN);
   if (rc) return rc;
   const int smem = TC_STAGES * TC_STAGE_BYTES + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
