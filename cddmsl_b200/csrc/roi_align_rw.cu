@@ -33,7 +33,8 @@ int launch_transpose(const float* in, float* out, int N, int A, int B, cudaStrea
 namespace {
 
 constexpr int kRwP = 14;
-// CPL channels per lane.  CPL = 1 (default): 16 warps x ring of 3 boxes (128 registers);  CPL = 2 (C % 64 == 0, knob):
+// CPL channels per lane.  CPL = 1 (default): 16 warps x ring of 3 boxes (128 registers; measured alternatives on the
+// VOC shape: 12 warps x ring of 4 at 141 registers 2.23 ms, 20 warps x ring of 2 at 96 registers 2.16 ms, this 1.97 ms);  CPL = 2 (C % 64 == 0, knob):
 // every tap, flag test and branch serves two channels -- 12 warps x ring of 2 boxes of 64 channels (168 registers).
 template <int CPL>
 struct RwCfg;
