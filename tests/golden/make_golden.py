@@ -35,6 +35,9 @@ What it records (all seeded, fp32 / int64):
   * pretrain_ref.npz — RegionCLIP pretraining losses: the literal lines `clip_rcnn.py:590-611`, `:624-640` and the
     literal class `MILCrossEntropy` (`utils/comm.py:332-355`) executed on seeded tensors.
 
+  * inference_ref.npz — test-time post-processing: the reference's own `fast_rcnn_inference_single_image` on its own
+    `Boxes` / `Instances` / `batched_nms` (all loaded verbatim, torchvision CPU underneath).
+
 The tests never read /root/reference; they read these files.
 """
 import importlib.util
@@ -407,6 +410,62 @@ def head_ref_cases():
     print("head_ref:", sorted(k for k in out if k.startswith("loss_")))
 
 
+def inference_ref_cases():
+    """inference_ref.npz: the reference's OWN `fast_rcnn_inference_single_image` (fast_rcnn.py:101-209, loaded verbatim)
+    running on its own `Boxes` / `Instances` (structures/boxes.py, instances.py, verbatim) and its own `batched_nms`
+    (layers/nms.py, verbatim, over torchvision CPU): class-specific and class-agnostic boxes, non-finite rows, a
+    threshold nothing passes, `vis` scores, no top-k limit."""
+    def nonzero_tuple(x):
+        return x.nonzero().unbind(1) if x.dim() else x.unsqueeze(0).nonzero().unbind(1)
+
+    base = {"detectron2": {}, "detectron2.layers": {"nonzero_tuple": nonzero_tuple, "cat": torch.cat},
+            "detectron2.utils": {}, "detectron2.utils.env": {"TORCH_VERSION": (2, 0)}}
+    ref_b = _load_with_stubs("ref_boxes_inf", "detectron2/structures/boxes.py", base)
+    ref_i = _load_with_stubs("ref_instances_inf", "detectron2/structures/instances.py", {})
+    import types
+    # (nms.py binds the rotated-box op at import time: give it the pre-1.7 branch with a placeholder extension module)
+    ref_n = _load_with_stubs("ref_nms_inf", "detectron2/layers/nms.py", {
+        "detectron2": {"_C": types.SimpleNamespace(nms_rotated=None)}, "detectron2.utils": {},
+        "detectron2.utils.env": {"TORCH_VERSION": (1, 6)}})
+    storage = _RecordingStorage()
+    ref, _, _ = _load_ref_fast_rcnn(storage)
+    ref.Boxes, ref.Instances, ref.batched_nms = ref_b.Boxes, ref_i.Instances, ref_n.batched_nms
+    g = synth.generator(41)
+    shape = (600, 1000)
+    cases = {  # name: (R, K, per-class boxes, score_thresh, nms_thresh, topk, vis, poison rows)
+        "perclass": (200, 20, True, 0.05, 0.5, 100, False, 0),
+        "agnostic": (300, 8, False, 0.3, 0.5, 10, False, 0),
+        "nonfinite": (120, 6, True, 0.05, 0.6, 50, False, 5),
+        "nothing": (64, 5, True, 2.0, 0.5, 100, False, 0),
+        "vis": (150, 10, False, 0.05, 0.4, 30, True, 0),
+        "nolimit": (1000, 3, True, 0.2, 0.7, -1, False, 0),
+    }
+    out = {"names": np.array(list(cases))}
+    for name, (r, k, per_class, st, nt, topk, vis, poison) in cases.items():
+        centre = synth.make_boxes(r, shape[0], shape[1], g, degenerate_frac=0.0)
+        if per_class:
+            boxes = (centre[:, None, :] + torch.randn(r, k, 4, generator=g) * 8.0).reshape(r, k * 4)
+        else:
+            boxes = centre.clone()
+        boxes[: r // 4] = boxes[r // 4: 2 * (r // 4)] + torch.randn_like(boxes[: r // 4]) * 3.0   # overlapping groups
+        scores = torch.softmax(torch.randn(r, k + 1, generator=g) * 2.5, dim=1)
+        sbf = torch.softmax(torch.randn(r, k + 1, generator=g) * 2.5, dim=1)
+        if poison:
+            boxes[3, 1] = float("nan")
+            boxes[17, 0] = float("inf")
+            scores[29, 2] = float("nan")
+            scores[44, 0] = float("inf")
+            boxes[60, 3] = float("-inf")
+        res, kept = ref.fast_rcnn_inference_single_image(boxes.clone(), scores.clone(), shape, st, nt, False, "gaussian",
+                                                         0.5, 0.001, topk, sbf.clone(), vis)
+        out.update({f"boxes_{name}": boxes.numpy(), f"scores_{name}": scores.numpy(), f"sbf_{name}": sbf.numpy(),
+                    f"params_{name}": np.array([st, nt, topk, float(vis)]),
+                    f"pred_boxes_{name}": res.pred_boxes.tensor.numpy(), f"pred_scores_{name}": res.scores.numpy(),
+                    f"pred_classes_{name}": res.pred_classes.numpy(), f"kept_{name}": kept.numpy()})
+        print("inference_ref", name, "detections", len(kept))
+    np.savez_compressed(os.path.join(HERE, "inference_ref.npz"), **out)
+
+
 def _ref_lines(rel, first, last):
     with open(os.path.join(REF, rel)) as fh:
         lines = fh.read().splitlines()[first - 1:last]
@@ -562,9 +621,11 @@ def pretrain_ref_cases():
 
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
-    if len(sys.argv) > 1 and sys.argv[1] in ("box_reg", "match", "head_ref", "align_ref", "pretrain_ref"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("box_reg", "match", "head_ref", "align_ref", "pretrain_ref",
+                                             "inference_ref"):
         {"box_reg": box_reg_cases, "match": match_cases, "head_ref": head_ref_cases,
-         "align_ref": align_ref_cases, "pretrain_ref": pretrain_ref_cases}[sys.argv[1]]()
+         "align_ref": align_ref_cases, "pretrain_ref": pretrain_ref_cases,
+         "inference_ref": inference_ref_cases}[sys.argv[1]]()
         sys.exit(0)
     roi_cases()
     nms_cases()
@@ -575,5 +636,6 @@ if __name__ == "__main__":
     head_ref_cases()
     align_ref_cases()
     pretrain_ref_cases()
+    inference_ref_cases()
     sizes = {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")}
     print(sizes, sum(sizes.values()))

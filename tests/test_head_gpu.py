@@ -296,3 +296,31 @@ def test_box_reg_loss_through_predictor_matches_oracle_and_is_sync_free():
                                                       torch.zeros(0, dtype=torch.int64, device=DEV), 3,
                                                       [10.0, 10.0, 5.0, 5.0], 0.5, True)
     assert z.item() == 0.0
+
+
+def test_inference_equals_reference_fast_rcnn_inference(golden_dir):
+    """a6: `fast_rcnn_inference_single_image` (fast_rcnn.py:130-209) against outputs of the reference's own function on
+    its own Boxes / Instances / batched_nms (tests/golden/make_golden.py:inference_ref_cases): kept rows and classes
+    identical, boxes and scores bit-equal."""
+    from cddmsl_b200.modeling.fast_rcnn import fast_rcnn_inference, fast_rcnn_inference_single_image
+
+    f = np.load(os.path.join(golden_dir, "inference_ref.npz"))
+    names = [str(n) for n in f["names"]]
+    assert len(names) == 6
+    per_image = {}
+    for name in names:
+        st, nt, topk, vis = (float(v) for v in f[f"params_{name}"])
+        boxes, scores, sbf = (torch.from_numpy(f[f"{k}_{name}"]).to(DEV) for k in ("boxes", "scores", "sbf"))
+        res, kept = fast_rcnn_inference_single_image(boxes, scores, (600, 1000), st, nt, False, "gaussian", 0.5, 0.001,
+                                                     int(topk), sbf, bool(vis))
+        assert np.array_equal(kept.cpu().numpy(), f[f"kept_{name}"]), name
+        assert np.array_equal(res.pred_classes.cpu().numpy(), f[f"pred_classes_{name}"]), name
+        assert np.array_equal(res.pred_boxes.tensor.cpu().numpy(), f[f"pred_boxes_{name}"]), name
+        assert np.array_equal(res.scores.cpu().numpy(), f[f"pred_scores_{name}"]), name
+        per_image[name] = (boxes, scores, sbf)
+    # the list form (fast_rcnn.py:42-98) over two images with the same settings
+    a, b = per_image["perclass"], per_image["perclass"]
+    st, nt, topk, _ = (float(v) for v in f["params_perclass"])
+    res, kept = fast_rcnn_inference([a[0], b[0]], [a[1], b[1]], [(600, 1000)] * 2, st, nt, topk_per_image=int(topk))
+    for i in range(2):
+        assert np.array_equal(kept[i].cpu().numpy(), f["kept_perclass"])
