@@ -167,6 +167,42 @@ def test_row_walk_backward(channels, sr, aligned):
     assert not np.array_equal(gin, gin_cl)   # two different kernels ran
 
 
+def test_row_walk_backward_fuzz_against_channels_last():
+    """40 random shapes (maps down to 1 x 1, C = 32 ... 128, any sampling ratio, legacy and aligned coordinates, boxes
+    far outside the map, zero-area boxes): the row-walk backward and the round-1 channels-last backward are two
+    independent implementations of the same sum and have to agree to 1e-4 of the gradient scale."""
+    from cddmsl_b200 import _lib, ops
+
+    rng = np.random.RandomState(7)
+    g = synth.generator(99)
+    for trial in range(40):
+        n = int(rng.randint(1, 4))
+        c = int(rng.choice([32, 64, 96, 128]))
+        h, w = int(rng.choice([1, 2, 3, 7, 20, 38, 50])), int(rng.choice([1, 2, 5, 16, 63, 90]))
+        r = int(rng.randint(1, 60))
+        sr = int(rng.choice([0, 0, 0, 1, 2, 3]))
+        aligned = bool(rng.randint(0, 2))
+        cx, cy = rng.uniform(-0.3, 1.3, r) * w * 16, rng.uniform(-0.3, 1.3, r) * h * 16
+        bw = np.exp(rng.uniform(np.log(1.0), np.log(max(w * 16 * 1.5, 2.0)), r))
+        bh = np.exp(rng.uniform(np.log(1.0), np.log(max(h * 16 * 1.5, 2.0)), r))
+        rois = np.stack([rng.randint(0, n, r).astype(np.float64), cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+        zero = rng.rand(r) < 0.06
+        rois[zero, 3] = rois[zero, 1]                      # zero width
+        rois = torch.from_numpy(rois.astype(np.float32)).to(DEV)
+        gout = torch.randn(r, c, 14, 14, generator=g).to(DEV)
+        _lib.tune("roi_rw_min_units", 0)
+        try:
+            a = ops.roi_align_backward(gout, rois, 1.0 / 16, 14, 14, n, c, h, w, sr, aligned)
+            _lib.tune("roi_rw", 0)
+            b = ops.roi_align_backward(gout, rois, 1.0 / 16, 14, 14, n, c, h, w, sr, aligned)
+        finally:
+            _lib.tune("roi_rw", 1)
+            _lib.tune("roi_rw_min_units", 65536)
+        scale = max(float(b.abs().max()), 1e-6)
+        err = float((a - b).abs().max())
+        assert err <= 1e-4 * scale, (trial, n, c, h, w, r, sr, aligned, err, scale)
+
+
 def test_wide_bands_and_sparse_sampling_grids():
     """Plane-resident classes beyond the common ones: RoIs wider than 6 cells per bin (B halves of the records), a
     fixed sampling grid on huge bins (per-sample path), boxes hanging over every border, on a map with H*W odd."""
