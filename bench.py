@@ -387,11 +387,18 @@ def extra_sections(args, rank, world, dev, ops, dist, peak):
     counts = torch.full((nb,), m, dtype=torch.int32, device=dev)
     keep, nk = batched_nms_images(boxes, scores, None, counts, 0.7)
     t_b = timed_median(lambda: batched_nms_images(boxes, scores, None, counts, 0.7), 10)
+    # what find_top_rpn_proposals asks for: only the first post_nms_topk = 2000 kept boxes per image (train setting)
+    keep2, nk2 = batched_nms_images(boxes, scores, None, counts, 0.7, max_keep=2000)
+    prefix_ok = all(bool(torch.equal(keep2[i, : int(nk2[i])], keep[i, : int(nk2[i])])) and int(nk2[i]) == min(2000, int(nk[i]))
+                    for i in range(nb))
+    t_k = timed_median(lambda: batched_nms_images(boxes, scores, None, counts, 0.7, max_keep=2000), 10)
     t_1 = timed_median(lambda: batched_nms(boxes[0], scores[0], torch.zeros(m, dtype=torch.int64, device=dev), 0.7), 10)
     nms_bytes = nb * (28 * m + 8 * m * ((m + 63) // 64))
     ex["nms"] = {"workload": f"RPN batch {nb} x {m} boxes, IoU 0.7, one class (C4: one level)", "ms": round(t_b, 4),
                  "boxes_per_s": nb * m / (t_b * 1e-3), "kept_per_image_mean": float(nk.float().mean()),
                  "single_image_12000_ms": round(t_1, 4), "algorithmic_bytes": nms_bytes,
+                 "post_nms_topk_2000_ms": round(t_k, 4), "post_nms_topk_2000_boxes_per_s": nb * m / (t_k * 1e-3),
+                 "post_nms_topk_2000_is_prefix_of_full": prefix_ok,
                  "gbs": nms_bytes / (t_b * 1e-3) / 1e9, "frac_of_hbm_peak": nms_bytes / (t_b * 1e-3) / 1e9 / peak,
                  "bound": "the greedy scan (serial over 64-box blocks), not bandwidth (SURVEY 8d)"}
     ex["_nms_spot"] = (boxes[0, :3000].cpu(), scores[0, :3000].cpu())

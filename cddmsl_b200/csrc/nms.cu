@@ -112,6 +112,9 @@ __device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float a
   const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
+  // disjoint boxes (the vast majority of pairs): 0 / union is 0, or NaN for 0 / 0 -- never above a non-negative
+  // threshold.  Same verdict as the division below, without the IEEE divide.
+  if (inter == 0.f && thr_dn >= 0.f) return false;
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
   // (double)ovr > thr  <=>  ovr > thr_dn with thr_dn = the largest float <= thr (round_down_threshold): exact, and
   // keeps the comparison off the FP64 pipe.  NaN (0/0) compares false: never suppresses.
@@ -122,14 +125,13 @@ __device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float a
 // Row masks: mask[i][cb] bit j = box (cb*64+j) is suppressed by box i (j > i inside a diagonal tile).
 // Diagonal tiles additionally emit the COLUMN view through warp ballots: coldiag[rb*64+j] bit i = row i (< j, same
 // tile) suppresses j — what the scan kernel's ballot fix-point needs.
-__global__ void __launch_bounds__(kTile)
-nms_mask_kernel(const float4* __restrict__ sboxes_all, const int* __restrict__ scls_all,
-                const int32_t* __restrict__ counts, int m_fixed, int m_max, float thr, int col_blocks,
-                unsigned long long* __restrict__ mask_all, unsigned long long* __restrict__ coldiag_all) {
+// one 64 x 64 tile (rb, cb) of image img; M = boxes of the image that take part.  Called by all 64 threads of a CTA.
+__device__ __forceinline__ void nms_mask_tile(const float4* __restrict__ sboxes_all, const int* __restrict__ scls_all,
+                                              int m_max, float thr, int col_blocks,
+                                              unsigned long long* __restrict__ mask_all,
+                                              unsigned long long* __restrict__ coldiag_all, int img, int M, int rb,
+                                              int cb) {
   // col_blocks = ceil(m_max / 64): row stride of the mask for every image
-  const int img = blockIdx.z;
-  const int M = image_count(counts, img, m_fixed, m_max);
-  const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb || cb * kTile >= M) return;
   const float4* sboxes = sboxes_all + (size_t)img * m_max;
   const int* scls = scls_all + (size_t)img * m_max;
@@ -174,6 +176,36 @@ nms_mask_kernel(const float4* __restrict__ sboxes_all, const int* __restrict__ s
       (unsigned long long)colpart[0][threadIdx.x] | ((unsigned long long)colpart[1][threadIdx.x] << 32);
 }
 
+
+// m_limit: only the m_limit best-scoring boxes of an image take part (top-k-limited NMS, see nms_run)
+__global__ void __launch_bounds__(kTile)
+nms_mask_kernel(const float4* __restrict__ sboxes_all, const int* __restrict__ scls_all,
+                const int32_t* __restrict__ counts, int m_fixed, int m_max, float thr, int col_blocks,
+                unsigned long long* __restrict__ mask_all, unsigned long long* __restrict__ coldiag_all, int m_limit) {
+  const int img = blockIdx.z;
+  const int M = min(image_count(counts, img, m_fixed, m_max), m_limit);
+  nms_mask_tile(sboxes_all, scls_all, m_max, thr, col_blocks, mask_all, coldiag_all, img, M, blockIdx.y, blockIdx.x);
+}
+
+// The full pass behind a top-k-limited first pass: normally no image needs it, and a grid of col_blocks^2 x B CTAs that
+// all exit at once still costs 0.29 ms (RPN batch 16 x 12 000).  So a small fixed grid looks at the per-image flags
+// and walks the tiles of the images that do need the full mask.
+__global__ void __launch_bounds__(kTile)
+nms_mask_needed_kernel(const float4* __restrict__ sboxes_all, const int* __restrict__ scls_all,
+                       const int32_t* __restrict__ counts, int m_fixed, int m_max, float thr, int col_blocks,
+                       unsigned long long* __restrict__ mask_all, unsigned long long* __restrict__ coldiag_all, int B,
+                       const int32_t* __restrict__ need) {
+  for (int img = 0; img < B; ++img) {
+    if (!need[img]) continue;
+    const int M = image_count(counts, img, m_fixed, m_max);
+    const int nblk = (M + kTile - 1) / kTile;
+    for (int t = blockIdx.x; t < nblk * nblk; t += gridDim.x) {
+      nms_mask_tile(sboxes_all, scls_all, m_max, thr, col_blocks, mask_all, coldiag_all, img, M, t / nblk, t % nblk);
+      __syncthreads();  // the tile's shared arrays are reused by the next one
+    }
+  }
+}
+
 // One CTA, 1024 threads.  remv[] (shared) = bitmap of suppressed boxes.  Per 64-box block b:
 //   * warp 0 resolves the block with a ballot fix-point on the column masks: kept_{n+1} = alive & ~{ j : some kept_n
 //     row i < j suppresses j } — its unique fixed point is the greedy result, reached in (longest suppression chain
@@ -184,10 +216,13 @@ nms_mask_kernel(const float4* __restrict__ sboxes_all, const int* __restrict__ s
 __global__ void __launch_bounds__(1024)
 nms_scan_kernel(const unsigned long long* __restrict__ mask_all, const unsigned long long* __restrict__ coldiag_all,
                 const int* __restrict__ order_all, const int32_t* __restrict__ counts, int m_fixed, int m_max,
-                int stride_blocks, int64_t* __restrict__ keep_all, int32_t* __restrict__ num_keep_all) {
+                int stride_blocks, int64_t* __restrict__ keep_all, int32_t* __restrict__ num_keep_all, int m_limit,
+                int max_keep, const int32_t* __restrict__ need_in, int32_t* __restrict__ need_out) {
   extern __shared__ unsigned long long remv[];  // [stride_blocks]
   const int img = blockIdx.x;
-  const int M = image_count(counts, img, m_fixed, m_max);
+  if (need_in && !need_in[img]) return;   // the limited pass already produced max_keep boxes for this image
+  const int m_full = image_count(counts, img, m_fixed, m_max);
+  const int M = min(m_full, m_limit);
   const int col_blocks = (M + kTile - 1) / kTile;  // this image's blocks; rows are stride_blocks words apart
   const unsigned long long* mask = mask_all + (size_t)img * m_max * stride_blocks;
   const unsigned long long* coldiag = coldiag_all + (size_t)img * stride_blocks * kTile;
@@ -272,9 +307,15 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask_all, const unsigned 
     __syncthreads();
     if (threadIdx.x == 0) count_s = base + __popcll(kept);
     // (count_s and kept_s are next touched after the barrier above / the next iteration's barrier)
+    if (max_keep > 0 && base + __popcll(kept) >= max_keep) break;  // uniform: the caller wants no more than max_keep
   }
   __syncthreads();
-  if (threadIdx.x == 0) *num_keep = count_s;
+  if (threadIdx.x == 0) {
+    const int total = count_s;
+    *num_keep = max_keep > 0 ? min(total, max_keep) : total;
+    // the limited pass ran out of boxes before max_keep were kept: the full pass has to redo this image
+    if (need_out) need_out[img] = (max_keep > 0 && total < max_keep && M < m_full) ? 1 : 0;
+  }
 }
 
 struct NmsWs {
@@ -289,6 +330,7 @@ struct NmsWs {
   int* seg_end;
   unsigned long long* mask;
   unsigned long long* coldiag;
+  int32_t* need;           // top-k-limited NMS: images the limited pass could not finish
   void* cub_temp;
   size_t cub_bytes;
   size_t total;
@@ -316,6 +358,7 @@ static NmsWs carve(void* base, int64_t B, int64_t M) {
   w.seg_end = (int*)take(b * 4);
   w.mask = (unsigned long long*)take(b * m * cb * 8);
   w.coldiag = (unsigned long long*)take(b * cb * kTile * 8);
+  w.need = (int32_t*)take(b * 4);
   w.cub_bytes = 0;
   if (b == 1) {
     cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const float*)nullptr, (float*)nullptr,
@@ -341,9 +384,14 @@ static float round_down_threshold(double t) {
 }
 
 // B images, padded to m_max boxes each; counts == nullptr: every image holds exactly m_max boxes (the B = 1 call)
+// max_keep > 0: only the first max_keep entries of the keep list are wanted (find_top_rpn_proposals keeps
+// post_nms_topk = 1000 / 2000 of up to 12 000 candidates, proposal_utils.py:116-118).  Greedy NMS never looks ahead,
+// so those entries depend on the best-scoring boxes only: a first pass works on the top 2 * max_keep boxes (mask work
+// falls with the square of that), and a second pass over everything runs only for the images where the first one ran
+// out of boxes before max_keep were kept (decided on the device: no host synchronisation).
 static int nms_run(const float* boxes, const float* scores, const int64_t* idxs, const int32_t* counts, int B,
                    int m_max, double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep, const NmsWs& w,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int max_keep = 0) {
   const int col_blocks = ceil_div(m_max, kTile);
   if ((size_t)col_blocks * 8 > 200 * 1024) return CDDMSL_EINVAL;  // removed-bitmap must fit shared memory
   if (idxs && coord_trick) {
@@ -368,15 +416,29 @@ static int nms_run(const float* boxes, const float* scores, const int64_t* idxs,
       reinterpret_cast<const float4*>(boxes), idxs, w.order, w.max_coord, coord_trick, w.sboxes, w.scls, counts,
       m_max, m_max);
   count_launch();
-  nms_mask_kernel<<<dim3(col_blocks, col_blocks, B), kTile, 0, stream>>>(w.sboxes, w.scls, counts, m_max, m_max,
-                                                                         round_down_threshold(iou_threshold), col_blocks, w.mask,
-                                                                         w.coldiag);
-  count_launch();
+  const float thr = round_down_threshold(iou_threshold);
   const int smem = col_blocks * 8;
   if (smem > 48 * 1024)
     CDDMSL_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int m_first = max_keep > 0 ? min(m_max, ceil_div(2 * max_keep, kTile) * kTile) : m_max;
+  const bool limited = m_first < m_max;
+  if (limited) {
+    const int cb1 = ceil_div(m_first, kTile);
+    nms_mask_kernel<<<dim3(cb1, cb1, B), kTile, 0, stream>>>(w.sboxes, w.scls, counts, m_max, m_max, thr, col_blocks,
+                                                             w.mask, w.coldiag, m_first);
+    nms_scan_kernel<<<B, 1024, smem, stream>>>(w.mask, w.coldiag, w.order, counts, m_max, m_max, col_blocks, keep,
+                                               num_keep, m_first, max_keep, nullptr, w.need);
+    count_launch(2);
+  }
+  if (limited)
+    nms_mask_needed_kernel<<<sm_count() * 16, kTile, 0, stream>>>(w.sboxes, w.scls, counts, m_max, m_max, thr,
+                                                                 col_blocks, w.mask, w.coldiag, B, w.need);
+  else
+    nms_mask_kernel<<<dim3(col_blocks, col_blocks, B), kTile, 0, stream>>>(w.sboxes, w.scls, counts, m_max, m_max, thr,
+                                                                           col_blocks, w.mask, w.coldiag, m_max);
+  count_launch();
   nms_scan_kernel<<<B, 1024, smem, stream>>>(w.mask, w.coldiag, w.order, counts, m_max, m_max, col_blocks, keep,
-                                             num_keep);
+                                             num_keep, m_max, max_keep, limited ? w.need : nullptr, nullptr);
   count_launch();
   CDDMSL_CHECK_LAUNCH();
   return CDDMSL_OK;
@@ -388,9 +450,20 @@ using namespace cddmsl;
 
 extern "C" size_t cddmsl_nms_workspace_bytes(int64_t M) { return carve(nullptr, 1, M).total; }
 
+extern "C" int cddmsl_nms_topk(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
+                               double iou_threshold, int coord_trick, int max_keep, int64_t* keep, int32_t* num_keep,
+                               void* workspace, size_t workspace_bytes, cddmsl_stream_t stream_);
+
 extern "C" int cddmsl_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
                           double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep, void* workspace,
                           size_t workspace_bytes, cddmsl_stream_t stream_) {
+  return cddmsl_nms_topk(boxes, scores, idxs, M, iou_threshold, coord_trick, 0, keep, num_keep, workspace,
+                         workspace_bytes, stream_);
+}
+
+extern "C" int cddmsl_nms_topk(const float* boxes, const float* scores, const int64_t* idxs, int64_t M,
+                               double iou_threshold, int coord_trick, int max_keep, int64_t* keep, int32_t* num_keep,
+                               void* workspace, size_t workspace_bytes, cddmsl_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (M < 0 || !num_keep) return CDDMSL_EINVAL;
   if (M == 0) {
@@ -403,17 +476,31 @@ extern "C" int cddmsl_nms(const float* boxes, const float* scores, const int64_t
     return CDDMSL_EALIGN;
   NmsWs w = carve(workspace, 1, M);
   if (w.total > workspace_bytes) return CDDMSL_EWORKSPACE;
-  return nms_run(boxes, scores, idxs, nullptr, 1, (int)M, iou_threshold, coord_trick, keep, num_keep, w, stream);
+  return nms_run(boxes, scores, idxs, nullptr, 1, (int)M, iou_threshold, coord_trick, keep, num_keep, w, stream,
+                 max_keep);
 }
 
 extern "C" size_t cddmsl_nms_batched_workspace_bytes(int B, int64_t Mmax) {
   return carve(nullptr, B < 2 ? 2 : B, Mmax).total;
 }
 
+extern "C" int cddmsl_nms_batched_topk(const float* boxes, const float* scores, const int64_t* idxs,
+                                       const int32_t* counts, int B, int64_t Mmax, double iou_threshold,
+                                       int coord_trick, int max_keep, int64_t* keep, int32_t* num_keep,
+                                       void* workspace, size_t workspace_bytes, cddmsl_stream_t stream_);
+
 extern "C" int cddmsl_nms_batched(const float* boxes, const float* scores, const int64_t* idxs,
                                   const int32_t* counts, int B, int64_t Mmax, double iou_threshold, int coord_trick,
                                   int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
                                   cddmsl_stream_t stream_) {
+  return cddmsl_nms_batched_topk(boxes, scores, idxs, counts, B, Mmax, iou_threshold, coord_trick, 0, keep, num_keep,
+                                 workspace, workspace_bytes, stream_);
+}
+
+extern "C" int cddmsl_nms_batched_topk(const float* boxes, const float* scores, const int64_t* idxs,
+                                       const int32_t* counts, int B, int64_t Mmax, double iou_threshold,
+                                       int coord_trick, int max_keep, int64_t* keep, int32_t* num_keep,
+                                       void* workspace, size_t workspace_bytes, cddmsl_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (B < 0 || Mmax < 0 || (B > 0 && !num_keep)) return CDDMSL_EINVAL;
   if (B == 0) return CDDMSL_OK;
@@ -428,5 +515,6 @@ extern "C" int cddmsl_nms_batched(const float* boxes, const float* scores, const
   const int bw = B < 2 ? 2 : B;  // the segmented sort also serves B == 1 with a device-side count
   NmsWs w = carve(workspace, bw, Mmax);
   if (w.total > workspace_bytes) return CDDMSL_EWORKSPACE;
-  return nms_run(boxes, scores, idxs, counts, B, (int)Mmax, iou_threshold, coord_trick, keep, num_keep, w, stream);
+  return nms_run(boxes, scores, idxs, counts, B, (int)Mmax, iou_threshold, coord_trick, keep, num_keep, w, stream,
+                 max_keep);
 }

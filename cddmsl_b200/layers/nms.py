@@ -25,23 +25,30 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
     return ops.batched_nms(boxes, scores, None, float(iou_threshold), False)
 
 
-def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float):
-    """Same as torchvision.ops.boxes.batched_nms, but safer (fp32 boxes)."""
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float,
+                max_keep: int = 0):
+    """Same as torchvision.ops.boxes.batched_nms, but safer (fp32 boxes).  `max_keep` > 0 (an extension): the caller
+    will slice the result to its first `max_keep` entries anyway (`keep[:topk_per_image]`, fast_rcnn.py:186-187), so
+    only that prefix is produced -- bit-identical, the kernels look at the best-scoring candidates first."""
     assert boxes.shape[-1] == 4
     trick = len(boxes) < 40000 and boxes.numel() <= COORD_TRICK_NUMEL_LIMIT
-    return ops.batched_nms(boxes.float(), scores, idxs, float(iou_threshold), bool(trick))
+    return ops.batched_nms(boxes.float(), scores, idxs, float(iou_threshold), bool(trick), int(max_keep))
 
 
-def batched_nms_images(boxes: torch.Tensor, scores: torch.Tensor, idxs, counts: torch.Tensor, iou_threshold: float):
+def batched_nms_images(boxes: torch.Tensor, scores: torch.Tensor, idxs, counts: torch.Tensor, iou_threshold: float,
+                       max_keep: int = 0):
     """`batched_nms` for the B images of a batch at once (the per-image loop of proposal_utils.py:42-66 in one launch
     sequence, no host sync).  boxes [B,M,4], scores [B,M], idxs [B,M] (or [M], shared by all images) or None,
     counts [B] on the device: image b uses its first counts[b] rows.  Returns (keep [B,M], num_keep [B]); per image
     the result is bit-identical to `batched_nms(boxes[b, :counts[b]], ...)`.
     The class-handling mode follows the same rule as `batched_nms`, evaluated on the padded size M (equal to the
-    per-image rule whenever nothing was filtered out; with a single class both modes give identical results)."""
+    per-image rule whenever nothing was filtered out; with a single class both modes give identical results).
+    `max_keep` > 0: only the first `max_keep` kept boxes of every image are wanted (the `[:post_nms_topk]` of
+    proposal_utils.py:116-118): the kernels then look at the best-scoring candidates first and stop early; the
+    returned prefix is bit-identical to the full result's."""
     assert boxes.shape[-1] == 4 and boxes.dim() == 3
     nb, m = scores.shape
     if idxs is not None and idxs.dim() == 1:
         idxs = idxs.unsqueeze(0).expand(nb, m)
     trick = m < 40000 and m * 4 <= COORD_TRICK_NUMEL_LIMIT
-    return ops.nms_images(boxes.float(), scores, idxs, counts, float(iou_threshold), bool(trick))
+    return ops.nms_images(boxes.float(), scores, idxs, counts, float(iou_threshold), bool(trick), int(max_keep))

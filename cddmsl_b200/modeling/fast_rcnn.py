@@ -125,7 +125,8 @@ def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, n
         boxes = boxes[filter_mask]
     scores = scores[filter_mask]
     scores_bf_multiply = scores_bf_multiply[filter_mask]
-    keep = batched_nms(boxes, scores, filter_inds[:, 1], nms_thresh)
+    # (only the first topk_per_image entries are used below: the kernels stop once they are known)
+    keep = batched_nms(boxes, scores, filter_inds[:, 1], nms_thresh, max_keep=max(int(topk_per_image), 0))
     if topk_per_image >= 0:
         keep = keep[:topk_per_image]
     boxes, scores, filter_inds = boxes[keep], scores[keep], filter_inds[keep]

@@ -49,7 +49,7 @@ def _per_image_batched(topk_proposals, topk_scores, level_ids, image_sizes, nms_
     scores = torch.gather(topk_scores, 1, perm)
     lvl = level_ids.to(torch.int64)[perm]
     counts = sel.sum(dim=1).to(torch.int32)
-    keep, num_keep = batched_nms_images(boxes, scores, lvl, counts, nms_thresh)
+    keep, num_keep = batched_nms_images(boxes, scores, lvl, counts, nms_thresh, max_keep=post_nms_topk)
     host = torch.cat([num_keep, valid.all().reshape(1).to(torch.int32)]).tolist()          # the one sync of the batch
     if training and not host[-1]:
         raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
@@ -155,7 +155,7 @@ def predict_proposals(anchors: List, pred_objectness_logits: List[torch.Tensor],
     boxes, scores, counts, fin = ops.rpn_decode_topk(an, pred_anchor_deltas[0].reshape(n, a_tot, 4), topk_idx,
                                                      topk_scores, hw, [float(v) for v in box2box_transform.weights],
                                                      float(box2box_transform.scale_clamp), float(min_box_size))
-    keep, num_keep = batched_nms_images(boxes, scores, None, counts, nms_thresh)
+    keep, num_keep = batched_nms_images(boxes, scores, None, counts, nms_thresh, max_keep=post_nms_topk)
     host = torch.cat([num_keep.to(torch.int32), fin]).tolist()       # the one sync of the batch
     if training and not host[-1]:
         raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")

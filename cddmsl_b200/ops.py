@@ -172,9 +172,10 @@ roi_align_pair.register_autograd(_roi_pair_bwd, setup_context=_roi_pair_setup)
 # ------------------------------------------------------------------------------------------------ NMS
 @torch.library.custom_op("cddmsl_b200::batched_nms", mutates_args=(), device_types="cuda")
 def batched_nms(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float,
-                coord_trick: bool) -> Tensor:
+                coord_trick: bool, max_keep: int = 0) -> Tensor:
     """Kept original indices, score-descending (ties: lower index first).  One device->host read of the
-    kept count sizes the result (the same sync PyTorch needs for any data-dependent shape)."""
+    kept count sizes the result (the same sync PyTorch needs for any data-dependent shape).
+    max_keep > 0: the first max_keep entries only (bit-identical prefix; the kernels stop early)."""
     _lib.require_cuda(boxes, "boxes")
     b = _f32c(boxes)
     s = _f32c(scores)
@@ -187,24 +188,25 @@ def batched_nms(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_thres
     nk = torch.empty((1,), dtype=torch.int32, device=b.device)
     ws = _ws(L.cddmsl_nms_workspace_bytes(m), b.device)
     with torch.cuda.device(b.device):
-        _lib.check(L.cddmsl_nms(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), m, float(iou_threshold), int(coord_trick),
-                                _lib.ptr(keep), _lib.ptr(nk), _lib.ptr(ws), ws.numel(),
-                                _lib.stream_ptr(b.device)), "nms")
+        _lib.check(L.cddmsl_nms_topk(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), m, float(iou_threshold),
+                                     int(coord_trick), int(max_keep), _lib.ptr(keep), _lib.ptr(nk), _lib.ptr(ws),
+                                     ws.numel(), _lib.stream_ptr(b.device)), "nms_topk")
     return keep[: int(nk.item())]
 
 
 @batched_nms.register_fake
-def _(boxes, scores, idxs, iou_threshold, coord_trick):
+def _(boxes, scores, idxs, iou_threshold, coord_trick, max_keep=0):
     n = torch.library.get_ctx().new_dynamic_size()
     return boxes.new_empty((n,), dtype=torch.int64)
 
 
 @torch.library.custom_op("cddmsl_b200::nms_images", mutates_args=(), device_types="cuda")
 def nms_images(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], counts: Tensor, iou_threshold: float,
-               coord_trick: bool) -> Tuple[Tensor, Tensor]:
+               coord_trick: bool, max_keep: int = 0) -> Tuple[Tensor, Tensor]:
     """NMS of B images in one launch sequence.  boxes [B,M,4], scores [B,M], idxs [B,M] or None, counts int32 [B]
     (device; image b uses its first counts[b] rows).  Returns (keep int64 [B,M], num_keep int32 [B]): keep[b, :num_keep[b]]
-    are the kept row indices of image b in score order.  No host sync here -- the caller decides when to read."""
+    are the kept row indices of image b in score order.  No host sync here -- the caller decides when to read.
+    max_keep > 0: only the first max_keep kept boxes per image are produced (bit-identical prefix of the full list)."""
     _lib.require_cuda(boxes, "boxes")
     b = _f32c(boxes)
     s = _f32c(scores)
@@ -219,14 +221,15 @@ def nms_images(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], counts: Te
     L = _lib.lib()
     ws = _ws(L.cddmsl_nms_batched_workspace_bytes(nb, m), b.device)
     with torch.cuda.device(b.device):
-        _lib.check(L.cddmsl_nms_batched(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), _lib.ptr(cnt), nb, m,
-                                        float(iou_threshold), int(coord_trick), _lib.ptr(keep), _lib.ptr(nk),
-                                        _lib.ptr(ws), ws.numel(), _lib.stream_ptr(b.device)), "nms_batched")
+        _lib.check(L.cddmsl_nms_batched_topk(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), _lib.ptr(cnt), nb, m,
+                                             float(iou_threshold), int(coord_trick), int(max_keep), _lib.ptr(keep),
+                                             _lib.ptr(nk), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(b.device)),
+                   "nms_batched_topk")
     return keep, nk
 
 
 @nms_images.register_fake
-def _(boxes, scores, idxs, counts, iou_threshold, coord_trick):
+def _(boxes, scores, idxs, counts, iou_threshold, coord_trick, max_keep=0):
     return scores.new_empty(scores.shape, dtype=torch.int64), scores.new_empty((scores.shape[0],), dtype=torch.int32)
 
 

@@ -79,6 +79,12 @@ size_t cddmsl_nms_workspace_bytes(int64_t M);
 int cddmsl_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t M, double iou_threshold,
                int coord_trick, int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
                cddmsl_stream_t stream);
+/* cddmsl_nms with an upper bound on the wanted keep list (`keep[:topk_per_image]`, fast_rcnn.py:186-187): the first
+ * max_keep entries of the full result, bit-identical; see cddmsl_nms_batched_topk.  max_keep <= 0: everything. */
+int cddmsl_nms_topk(const float* boxes, const float* scores, const int64_t* idxs, int64_t M, double iou_threshold,
+                    int coord_trick, int max_keep, int64_t* keep, int32_t* num_keep, void* workspace,
+                    size_t workspace_bytes, cddmsl_stream_t stream);
+
 
 /* The B images of one RPN batch in one call (the loop of proposal_utils.py:42-66 calls batched_nms once per image).
  * Padded layout: boxes [B][Mmax][4], scores [B][Mmax], idxs [B][Mmax] (nullable), counts int32[B] ON THE DEVICE
@@ -90,6 +96,16 @@ size_t cddmsl_nms_batched_workspace_bytes(int B, int64_t Mmax);
 int cddmsl_nms_batched(const float* boxes, const float* scores, const int64_t* idxs, const int32_t* counts, int B,
                        int64_t Mmax, double iou_threshold, int coord_trick, int64_t* keep, int32_t* num_keep,
                        void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+/* The same with an upper bound on the wanted keep list: only the first `max_keep` kept boxes of every image are
+ * produced (num_keep[b] <= max_keep; max_keep <= 0: all of them).  This is what find_top_rpn_proposals needs
+ * (`keep = keep[:post_nms_topk]`, detectron2/modeling/proposal_generator/proposal_utils.py:116-118): greedy NMS never
+ * looks ahead, so the first max_keep entries depend on the best-scoring boxes only -- a first pass works on the top
+ * 2*max_keep candidates, the full pass runs only for images where that was not enough (decided on the device).
+ * Results are bit-identical to the first max_keep entries of cddmsl_nms_batched.  Same workspace. */
+int cddmsl_nms_batched_topk(const float* boxes, const float* scores, const int64_t* idxs, const int32_t* counts, int B,
+                            int64_t Mmax, double iou_threshold, int coord_trick, int max_keep, int64_t* keep,
+                            int32_t* num_keep, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+
 
 /* Proposal pre-processing between the RPN head and NMS for a batch: RPN._decode_proposals
  * (proposal_generator/rpn.py:514-533) = Box2BoxTransform.apply_deltas (box_regression.py:77-117) on the pre-NMS

@@ -115,6 +115,57 @@ def test_large_single_image_bit_exact(m, k, thr):
     assert np.array_equal(got, _canon(want, scores.numpy()))
 
 
+@pytest.mark.parametrize("max_keep", [1, 64, 700, 2000, 5000])
+def test_topk_limited_batched_nms_is_a_prefix_of_the_full_result(max_keep):
+    """cddmsl_nms_batched_topk (`keep[:post_nms_topk]`, proposal_utils.py:116-118): bit-identical prefix of the full keep
+    list for every image -- images that finish inside the first pass (few overlaps), images that need the full pass
+    (heavily overlapping boxes: fewer than max_keep survive among the top 2*max_keep), short and empty images."""
+    from cddmsl_b200.layers import batched_nms_images
+
+    g = synth.generator(123)
+    m = 6000
+    bx, sc, counts = [], [], []
+    for i in range(5):
+        b, s, _ = synth.make_nms_inputs(m, 600, 1000, g, num_classes=1, tie_frac=0.01)
+        if i == 1:      # near-duplicates of 40 boxes: almost everything is suppressed
+            base = b[:40]
+            b = base[torch.randint(0, 40, (m,), generator=g)] + torch.randn(m, 4, generator=g) * 1.5
+        if i == 2:      # the best-scoring third is one tight cluster, the rest is spread out
+            o = torch.argsort(s, descending=True)[: m // 3]
+            b[o] = b[o[0]] + torch.randn(len(o), 4, generator=g) * 2.0
+        bx.append(b)
+        sc.append(s)
+        counts.append([m, m, m, 300, 0][i])
+    boxes, scores = torch.stack(bx).to(DEV), torch.stack(sc).to(DEV)
+    cnt = torch.tensor(counts, dtype=torch.int32, device=DEV)
+    full, nfull = batched_nms_images(boxes, scores, None, cnt, 0.7)
+    part, npart = batched_nms_images(boxes, scores, None, cnt, 0.7, max_keep=max_keep)
+    nfull, npart = nfull.tolist(), npart.tolist()
+    for i in range(5):
+        want = min(nfull[i], max_keep)
+        assert npart[i] == want, (i, npart[i], want)
+        assert torch.equal(part[i, :want], full[i, :want]), i
+    # and against the oracle for one image
+    ref = c_ref.batched_nms(bx[2].numpy(), sc[2].numpy(), np.zeros(m, np.int64), 0.7)
+    assert np.array_equal(part[2, : npart[2]].cpu().numpy(), _canon(ref, sc[2].numpy())[: npart[2]])
+
+
+@pytest.mark.parametrize("m,k,max_keep", [(20000, 20, 100), (5000, 8, 100), (3000, 3, 1000), (900, 1, 5)])
+def test_topk_limited_single_image_nms_is_a_prefix(m, k, max_keep):
+    """cddmsl_nms_topk (test-time `keep[:topk_per_image]`, fast_rcnn.py:186-187), class-aware and coordinate-trick modes."""
+    from cddmsl_b200.layers import batched_nms
+
+    g = synth.generator(321 + m)
+    boxes, scores, idxs = synth.make_nms_inputs(m, 600, 1000, g, num_classes=k, tie_frac=0.01)
+    if m == 5000:   # one class is a single tight cluster: the limited pass cannot fill max_keep from the top boxes alone
+        boxes[:] = boxes[0] + torch.randn(m, 4, generator=g) * 1.0
+    b, s, i = boxes.to(DEV), scores.to(DEV), idxs.to(DEV)
+    full = batched_nms(b, s, i, 0.5)
+    part = batched_nms(b, s, i, 0.5, max_keep=max_keep)
+    assert len(part) == min(len(full), max_keep)
+    assert torch.equal(part, full[: len(part)])
+
+
 def test_large_properties_256k():
     """configs[4] upper end (256k boxes): sorted by score, idempotent, and no kept pair overlaps above thr
     (checked on the top-scoring 4096 kept boxes with the exact fp32 formula)."""
