@@ -31,10 +31,10 @@ SIGNATURES = {
     "cddmsl_roi_align_bwd2": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     "cddmsl_nms_workspace_bytes": (_sz, [_i64]),
     "cddmsl_nms": (_i, [_vp, _vp, _vp, _i64, _d, _i, _vp, _vp, _vp, _sz, _vp]),
-    "cddmsl_nms_topk": (_i, [_vp, _vp, _vp, _i64, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "cddmsl_nms_topk": (_i, [_vp, _vp, _vp, _i64, _d, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cddmsl_nms_batched_workspace_bytes": (_sz, [_i, _i64]),
     "cddmsl_nms_batched": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _d, _i, _vp, _vp, _vp, _sz, _vp]),
-    "cddmsl_nms_batched_topk": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "cddmsl_nms_batched_topk": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _d, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cddmsl_rpn_decode_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp,
                                     _vp]),
     "cddmsl_clip_head_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -36,7 +36,7 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
 
 
 def batched_nms_images(boxes: torch.Tensor, scores: torch.Tensor, idxs, counts: torch.Tensor, iou_threshold: float,
-                       max_keep: int = 0):
+                       max_keep: int = 0, presorted: bool = False):
     """`batched_nms` for the B images of a batch at once (the per-image loop of proposal_utils.py:42-66 in one launch
     sequence, no host sync).  boxes [B,M,4], scores [B,M], idxs [B,M] (or [M], shared by all images) or None,
     counts [B] on the device: image b uses its first counts[b] rows.  Returns (keep [B,M], num_keep [B]); per image
@@ -45,10 +45,12 @@ def batched_nms_images(boxes: torch.Tensor, scores: torch.Tensor, idxs, counts: 
     per-image rule whenever nothing was filtered out; with a single class both modes give identical results).
     `max_keep` > 0: only the first `max_keep` kept boxes of every image are wanted (the `[:post_nms_topk]` of
     proposal_utils.py:116-118): the kernels then look at the best-scoring candidates first and stop early; the
-    returned prefix is bit-identical to the full result's."""
+    returned prefix is bit-identical to the full result's.  `presorted`: the caller guarantees non-increasing scores
+    per image (the sorted top-k of the RPN path): the internal stable sort is the identity and is skipped."""
     assert boxes.shape[-1] == 4 and boxes.dim() == 3
     nb, m = scores.shape
     if idxs is not None and idxs.dim() == 1:
         idxs = idxs.unsqueeze(0).expand(nb, m)
     trick = m < 40000 and m * 4 <= COORD_TRICK_NUMEL_LIMIT
-    return ops.nms_images(boxes.float(), scores, idxs, counts, float(iou_threshold), bool(trick), int(max_keep))
+    return ops.nms_images(boxes.float(), scores, idxs, counts, float(iou_threshold), bool(trick), int(max_keep),
+                          bool(presorted))

@@ -155,7 +155,8 @@ def predict_proposals(anchors: List, pred_objectness_logits: List[torch.Tensor],
     boxes, scores, counts, fin = ops.rpn_decode_topk(an, pred_anchor_deltas[0].reshape(n, a_tot, 4), topk_idx,
                                                      topk_scores, hw, [float(v) for v in box2box_transform.weights],
                                                      float(box2box_transform.scale_clamp), float(min_box_size))
-    keep, num_keep = batched_nms_images(boxes, scores, None, counts, nms_thresh, max_keep=post_nms_topk)
+    # `topk_scores` are sorted (proposal_utils.py:77-79) and the decode kernel compacts stably: no second sort
+    keep, num_keep = batched_nms_images(boxes, scores, None, counts, nms_thresh, max_keep=post_nms_topk, presorted=True)
     host = torch.cat([num_keep.to(torch.int32), fin]).tolist()       # the one sync of the batch
     if training and not host[-1]:
         raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")

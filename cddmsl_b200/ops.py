@@ -189,7 +189,7 @@ def batched_nms(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_thres
     ws = _ws(L.cddmsl_nms_workspace_bytes(m), b.device)
     with torch.cuda.device(b.device):
         _lib.check(L.cddmsl_nms_topk(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), m, float(iou_threshold),
-                                     int(coord_trick), int(max_keep), _lib.ptr(keep), _lib.ptr(nk), _lib.ptr(ws),
+                                     int(coord_trick), int(max_keep), 0, _lib.ptr(keep), _lib.ptr(nk), _lib.ptr(ws),
                                      ws.numel(), _lib.stream_ptr(b.device)), "nms_topk")
     return keep[: int(nk.item())]
 
@@ -202,11 +202,12 @@ def _(boxes, scores, idxs, iou_threshold, coord_trick, max_keep=0):
 
 @torch.library.custom_op("cddmsl_b200::nms_images", mutates_args=(), device_types="cuda")
 def nms_images(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], counts: Tensor, iou_threshold: float,
-               coord_trick: bool, max_keep: int = 0) -> Tuple[Tensor, Tensor]:
+               coord_trick: bool, max_keep: int = 0, presorted: bool = False) -> Tuple[Tensor, Tensor]:
     """NMS of B images in one launch sequence.  boxes [B,M,4], scores [B,M], idxs [B,M] or None, counts int32 [B]
     (device; image b uses its first counts[b] rows).  Returns (keep int64 [B,M], num_keep int32 [B]): keep[b, :num_keep[b]]
     are the kept row indices of image b in score order.  No host sync here -- the caller decides when to read.
-    max_keep > 0: only the first max_keep kept boxes per image are produced (bit-identical prefix of the full list)."""
+    max_keep > 0: only the first max_keep kept boxes per image are produced (bit-identical prefix of the full list).
+    presorted: the scores of every image are already non-increasing (the sort is skipped)."""
     _lib.require_cuda(boxes, "boxes")
     b = _f32c(boxes)
     s = _f32c(scores)
@@ -222,14 +223,15 @@ def nms_images(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], counts: Te
     ws = _ws(L.cddmsl_nms_batched_workspace_bytes(nb, m), b.device)
     with torch.cuda.device(b.device):
         _lib.check(L.cddmsl_nms_batched_topk(_lib.ptr(b), _lib.ptr(s), _lib.ptr(ids), _lib.ptr(cnt), nb, m,
-                                             float(iou_threshold), int(coord_trick), int(max_keep), _lib.ptr(keep),
-                                             _lib.ptr(nk), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(b.device)),
+                                             float(iou_threshold), int(coord_trick), int(max_keep), int(presorted),
+                                             _lib.ptr(keep), _lib.ptr(nk), _lib.ptr(ws), ws.numel(),
+                                             _lib.stream_ptr(b.device)),
                    "nms_batched_topk")
     return keep, nk
 
 
 @nms_images.register_fake
-def _(boxes, scores, idxs, counts, iou_threshold, coord_trick, max_keep=0):
+def _(boxes, scores, idxs, counts, iou_threshold, coord_trick, max_keep=0, presorted=False):
     return scores.new_empty(scores.shape, dtype=torch.int64), scores.new_empty((scores.shape[0],), dtype=torch.int32)
 
 

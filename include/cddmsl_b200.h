@@ -82,7 +82,7 @@ int cddmsl_nms(const float* boxes, const float* scores, const int64_t* idxs, int
 /* cddmsl_nms with an upper bound on the wanted keep list (`keep[:topk_per_image]`, fast_rcnn.py:186-187): the first
  * max_keep entries of the full result, bit-identical; see cddmsl_nms_batched_topk.  max_keep <= 0: everything. */
 int cddmsl_nms_topk(const float* boxes, const float* scores, const int64_t* idxs, int64_t M, double iou_threshold,
-                    int coord_trick, int max_keep, int64_t* keep, int32_t* num_keep, void* workspace,
+                    int coord_trick, int max_keep, int presorted, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, cddmsl_stream_t stream);
 
 
@@ -101,10 +101,13 @@ int cddmsl_nms_batched(const float* boxes, const float* scores, const int64_t* i
  * (`keep = keep[:post_nms_topk]`, detectron2/modeling/proposal_generator/proposal_utils.py:116-118): greedy NMS never
  * looks ahead, so the first max_keep entries depend on the best-scoring boxes only -- a first pass works on the top
  * 2*max_keep candidates, the full pass runs only for images where that was not enough (decided on the device).
- * Results are bit-identical to the first max_keep entries of cddmsl_nms_batched.  Same workspace. */
+ * Results are bit-identical to the first max_keep entries of cddmsl_nms_batched.  Same workspace.
+ * presorted != 0: the caller guarantees that the scores of every image are already non-increasing (the RPN path hands
+ * over its sorted top-k, proposal_utils.py:77-79); the stable sort is then the identity and is skipped. */
 int cddmsl_nms_batched_topk(const float* boxes, const float* scores, const int64_t* idxs, const int32_t* counts, int B,
-                            int64_t Mmax, double iou_threshold, int coord_trick, int max_keep, int64_t* keep,
-                            int32_t* num_keep, void* workspace, size_t workspace_bytes, cddmsl_stream_t stream);
+                            int64_t Mmax, double iou_threshold, int coord_trick, int max_keep, int presorted,
+                            int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                            cddmsl_stream_t stream);
 
 
 /* Proposal pre-processing between the RPN head and NMS for a batch: RPN._decode_proposals

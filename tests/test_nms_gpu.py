@@ -166,6 +166,28 @@ def test_topk_limited_single_image_nms_is_a_prefix(m, k, max_keep):
     assert torch.equal(part, full[: len(part)])
 
 
+def test_presorted_scores_skip_the_sort():
+    """`presorted` (the RPN path hands over its sorted top-k): identical to the call that sorts, incl. tied scores."""
+    from cddmsl_b200.layers import batched_nms_images
+
+    g = synth.generator(55)
+    m = 5000
+    bx, sc = [], []
+    for _ in range(3):
+        b, s, _ = synth.make_nms_inputs(m, 600, 1000, g, num_classes=1, tie_frac=0.05)
+        o = torch.sort(s, descending=True, stable=True).indices
+        bx.append(b[o])
+        sc.append(s[o])
+    boxes, scores = torch.stack(bx).to(DEV), torch.stack(sc).to(DEV)
+    cnt = torch.tensor([m, 4097, 1], dtype=torch.int32, device=DEV)
+    for max_keep in (0, 1000):
+        a, na = batched_nms_images(boxes, scores, None, cnt, 0.7, max_keep=max_keep)
+        b, nb = batched_nms_images(boxes, scores, None, cnt, 0.7, max_keep=max_keep, presorted=True)
+        assert torch.equal(na, nb)
+        for i, n in enumerate(na.tolist()):
+            assert torch.equal(a[i, :n], b[i, :n])
+
+
 def test_large_properties_256k():
     """configs[4] upper end (256k boxes): sorted by score, idempotent, and no kept pair overlaps above thr
     (checked on the top-scoring 4096 kept boxes with the exact fp32 formula)."""
