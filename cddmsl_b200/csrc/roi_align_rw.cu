@@ -35,7 +35,7 @@ namespace {
 constexpr int kRwP = 14;
 // CPL channels per lane.  CPL = 1 (default): 16 warps x ring of 3 boxes (128 registers; measured alternatives on the
 // VOC shape: 12 warps x ring of 4 at 141 registers 2.23 ms, 20 warps x ring of 2 at 96 registers 2.16 ms, this 1.97 ms);  CPL = 2 (C % 64 == 0, knob):
-// every tap, flag test and branch serves two channels -- 12 warps x ring of 2 boxes of 64 channels (168 registers).
+// every tap, flag test and branch serves two channels -- 9 warps x ring of 3 boxes of 64 channels (168 registers).
 template <int CPL>
 struct RwCfg;
 constexpr int kRwMaxG = 10;                      // samples per bin and axis the record holds (RoIs up to 140 cells)
@@ -57,7 +57,7 @@ struct RwCfg<1> {
 };
 template <>
 struct RwCfg<2> {
-  static constexpr int kWarps = 12, kNB = 2;
+  static constexpr int kWarps = 9, kNB = 3;
 };
 template <int CPL>
 struct RwLayout {
@@ -589,8 +589,9 @@ int g_roi_rw_min_units = 65536;  // below this many (RoI, 32-channel) units the 
                                  // persistent grid does not fill and the plan kernel's latency shows
                                  // ("roi_rw_min_units"; 1024 RoIs x 1024 channels: 0.45 ms there, 0.77 ms here)
 int g_roi_rw_cpl = 1;  // channels per lane ("roi_rw_cpl"; 2 needs C % 64 == 0).  Measured on the VOC shape: CPL = 2 executes
-                       // 23 % fewer instructions (0.90 G vs 1.17 G) but fits only 12 warps with a 2-deep ring -- 12 % of
-                       // its stall samples wait for the next box, issue slots 48 % busy vs 62 %: 2.37 ms against 2.10 ms
+                       // 23 % fewer instructions (0.90 G vs 1.17 G) but its 7 KB boxes leave room for fewer warps: 12 warps
+                       // with a 2-deep ring 2.37 ms (12 % of the stall samples wait for the next box), 9 warps with a
+                       // 3-deep ring 1.97 ms at one channel group per visit -- the same as CPL = 1 (1.96 ms), so no default
 
 template <int CPL, bool FIXED>
 int rw_launch(const float* gout, const float* rois, const unsigned char* recs, float* gt, unsigned* counter, int N,
