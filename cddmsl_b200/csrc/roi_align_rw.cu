@@ -583,8 +583,11 @@ roi_align_bwd_rw_kernel(const __grid_constant__ CUtensorMap gmap, const float* _
 }
 
 int g_roi_rw = 1;      // tuning knob "roi_rw": 1 = use this backward where eligible
-int g_roi_rw_k = 2;    // channel groups per visit of a RoI ("roi_rw_k"; VOC shape: 1 -> 1.98, 2 -> 1.97, 4 -> 2.09, 8 -> 2.68 ms;
-                       // an L2 evict_last hint on the REDs changes nothing, evict_first on the tile loads costs 0.1 ms)
+int g_roi_rw_k = 0;    // channel groups per visit of a RoI ("roi_rw_k"; 0 = automatic: 2, or 1 on maps of >= 4096 cells whose
+                       // RoIs are large).  Fine-grained visits balance the persistent warps:
+                       // VOC shape 1 -> 1.98, 2 -> 1.97, 4 -> 2.09, 8 -> 2.68 ms; Cityscapes shape 1 -> 3.73, 2 -> 3.96,
+                       // 4 -> 5.00 ms.  (An L2 evict_last hint on the REDs changes nothing, evict_first on the tile loads
+                       // costs 0.1 ms.)
 int g_roi_rw_min_units = 65536;  // below this many (RoI, 32-channel) units the channels-last kernel is faster: the
                                  // persistent grid does not fill and the plan kernel's latency shows
                                  // ("roi_rw_min_units"; 1024 RoIs x 1024 channels: 0.45 ms there, 0.77 ms here)
@@ -602,7 +605,7 @@ int rw_launch(const float* gout, const float* rois, const unsigned char* recs, f
                         CU_TENSOR_MAP_SWIZZLE_NONE))
     return kRwNoTensorMap;
   const int ngroups = C / (32 * CPL);
-  const int kgroups = min(g_roi_rw_k, ngroups);
+  const int kgroups = min(g_roi_rw_k > 0 ? g_roi_rw_k : (H * W >= 4096 ? 1 : 2), ngroups);
   const int vpr = ceil_div(ngroups, kgroups);
   auto k = roi_align_bwd_rw_kernel<CPL, FIXED>;
   static bool attr_set = false;
@@ -624,7 +627,7 @@ int rw_launch(const float* gout, const float* rois, const unsigned char* recs, f
 
 int tune_roi_rw(const char* key, int value) {
   if (!strcmp(key, "roi_rw")) g_roi_rw = value;
-  else if (!strcmp(key, "roi_rw_k")) g_roi_rw_k = value > 0 ? value : 1;
+  else if (!strcmp(key, "roi_rw_k")) g_roi_rw_k = value > 0 ? value : 0;
   else if (!strcmp(key, "roi_rw_min_units")) g_roi_rw_min_units = value;
   else if (!strcmp(key, "roi_rw_cpl")) g_roi_rw_cpl = value == 1 ? 1 : 2;
   else return 0;
