@@ -131,14 +131,6 @@ __device__ __forceinline__ void rw_wait(uint32_t a, uint32_t parity) {
 __device__ __forceinline__ void rw_red(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ void rw_red_if(bool on, float* p, float v) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.u32 q, %2, 0;\n\t"
-      "@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(p),
-      "f"(v), "r"((unsigned)on)
-      : "memory");
-}
 
 // same validity rule and weights as make_tap (roi_common.cuh); lo < 0: the sample contributes nothing
 struct RwTap {
