@@ -629,7 +629,8 @@ int tune_roi_rw(const char* key, int value) {
 bool roi_rw_eligible(int N, int C, int H, int W, int R, int P) {
   (void)N;
   return g_roi_rw && P == kRwP && C > 0 && C % 32 == 0 && (long long)H * W * C < 0x7fffffffLL &&
-         (long long)R * (C / 32) < 0x7fffffffLL && (long long)R * (C / 32) >= g_roi_rw_min_units;
+         (long long)R * C < 0x7fffffffLL /* TMA row coordinate r * C + c */ &&
+         (long long)R * (C / 32) >= g_roi_rw_min_units;
 }
 
 size_t roi_rw_workspace_bytes(int N, int C, int H, int W, int R) {
